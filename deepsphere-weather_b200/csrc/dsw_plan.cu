@@ -1,0 +1,284 @@
+// Plan construction: COO (int64, fp32) -> CSR + CSR^T (int32) + row-block union panels.
+// One-time setup per Laplacian / remap matrix; done on the host and uploaded.
+// Replaces the COO->CSR conversion torch.sparse.mm performs on every call
+// (reference modules/layers.py:164,167,962).
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "dsw_internal.cuh"
+
+namespace dsw {
+
+std::atomic<int64_t> g_launches{0};
+std::atomic<int> g_mix_mode{1};
+
+static thread_local cudaError_t t_last_err = cudaSuccess;
+void set_cuda_error(cudaError_t e) { t_last_err = e; }
+cudaError_t last_cuda_error() { return t_last_err; }
+
+struct HostCsr {
+  int32_t n_rows = 0, n_cols = 0;
+  std::vector<int32_t> rowptr, col;
+  std::vector<float> val;
+};
+
+// Stable counting sort by row, ascending column inside a row, duplicates summed.
+static HostCsr build_csr(int32_t n_rows, int32_t n_cols, int64_t nnz, const int64_t* r,
+                         const int64_t* c, const float* v) {
+  HostCsr out;
+  out.n_rows = n_rows;
+  out.n_cols = n_cols;
+  std::vector<int64_t> cnt(static_cast<size_t>(n_rows) + 1, 0);
+  for (int64_t i = 0; i < nnz; ++i) cnt[r[i] + 1]++;
+  for (int32_t i = 0; i < n_rows; ++i) cnt[i + 1] += cnt[i];
+  std::vector<int64_t> pos(cnt.begin(), cnt.end() - 1);
+  std::vector<std::pair<int32_t, float>> tmp(static_cast<size_t>(nnz));
+  for (int64_t i = 0; i < nnz; ++i) tmp[pos[r[i]]++] = {static_cast<int32_t>(c[i]), v[i]};
+  out.rowptr.assign(static_cast<size_t>(n_rows) + 1, 0);
+  out.col.reserve(nnz);
+  out.val.reserve(nnz);
+  for (int32_t row = 0; row < n_rows; ++row) {
+    auto b = tmp.begin() + cnt[row], e = tmp.begin() + cnt[row + 1];
+    std::stable_sort(b, e, [](const auto& x, const auto& y) { return x.first < y.first; });
+    for (auto it = b; it != e; ++it) {
+      if (!out.col.empty() && static_cast<int64_t>(out.col.size()) > out.rowptr[row] &&
+          out.col.back() == it->first) {
+        out.val.back() += it->second;  // coalesce duplicates
+      } else {
+        out.col.push_back(it->first);
+        out.val.push_back(it->second);
+      }
+    }
+    out.rowptr[row + 1] = static_cast<int32_t>(out.col.size());
+  }
+  return out;
+}
+
+static HostCsr transpose(const HostCsr& a) {
+  const int64_t nnz = static_cast<int64_t>(a.col.size());
+  std::vector<int64_t> r(nnz), c(nnz);
+  for (int32_t row = 0; row < a.n_rows; ++row)
+    for (int32_t e = a.rowptr[row]; e < a.rowptr[row + 1]; ++e) {
+      r[e] = a.col[e];
+      c[e] = row;
+    }
+  return build_csr(a.n_cols, a.n_rows, nnz, r.data(), c.data(), a.val.data());
+}
+
+struct HostRb {
+  int32_t R = 0, n_blocks = 0, max_union = 0;
+  std::vector<int32_t> blkptr, ucol;
+  std::vector<float> uval;
+};
+
+static HostRb build_rb(const HostCsr& a, int32_t R) {
+  HostRb rb;
+  rb.R = R;
+  rb.n_blocks = (a.n_rows + R - 1) / R;
+  rb.blkptr.assign(static_cast<size_t>(rb.n_blocks) + 1, 0);
+  std::vector<int32_t> uni;
+  for (int32_t blk = 0; blk < rb.n_blocks; ++blk) {
+    const int32_t r0 = blk * R, r1 = std::min(a.n_rows, r0 + R);
+    uni.assign(a.col.begin() + a.rowptr[r0], a.col.begin() + a.rowptr[r1]);
+    std::sort(uni.begin(), uni.end());
+    uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
+    const size_t base = rb.ucol.size();
+    rb.ucol.insert(rb.ucol.end(), uni.begin(), uni.end());
+    rb.uval.resize((base + uni.size()) * R, 0.f);
+    for (int32_t row = r0; row < r1; ++row)
+      for (int32_t e = a.rowptr[row]; e < a.rowptr[row + 1]; ++e) {
+        const size_t u = std::lower_bound(uni.begin(), uni.end(), a.col[e]) - uni.begin();
+        rb.uval[(base + u) * R + (row - r0)] = a.val[e];
+      }
+    rb.blkptr[blk + 1] = static_cast<int32_t>(rb.ucol.size());
+    rb.max_union = std::max<int32_t>(rb.max_union, static_cast<int32_t>(uni.size()));
+  }
+  return rb;
+}
+
+// Cost model (cycles per row-block per 64 features, one SM): gathers cost 2 cycles of the 128 B/clk
+// L1 path per union entry, FMAs cost R/2 cycles per union entry at 128 FMA/clk.
+static int32_t pick_rb_rows(const HostCsr& a) {
+  const int64_t nnz = static_cast<int64_t>(a.col.size());
+  if (a.n_rows < 8 || nnz == 0) return 0;
+  double best = 2.0 * nnz;  // plain CSR: L1-bound
+  int32_t best_r = 0;
+  for (int32_t R : {2, 4}) {
+    int64_t uni_total = 0;
+    std::vector<int32_t> uni;
+    for (int32_t r0 = 0; r0 < a.n_rows; r0 += R) {
+      const int32_t r1 = std::min(a.n_rows, r0 + R);
+      uni.assign(a.col.begin() + a.rowptr[r0], a.col.begin() + a.rowptr[r1]);
+      std::sort(uni.begin(), uni.end());
+      uni_total += std::unique(uni.begin(), uni.end()) - uni.begin();
+    }
+    const double cost = uni_total * std::max(2.0, 0.5 * R);
+    if (cost < 0.85 * best) {
+      best = cost;
+      best_r = R;
+    }
+  }
+  return best_r;
+}
+
+template <class T>
+static cudaError_t upload(T** dst, const std::vector<T>& src, cudaStream_t st) {
+  *dst = nullptr;
+  const size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(dst), bytes);
+  if (e != cudaSuccess) return e;
+  if (!src.empty()) e = cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+  return e;
+}
+
+static cudaError_t upload_csr(dsw_csr* d, const HostCsr& h, cudaStream_t st) {
+  d->n_rows = h.n_rows;
+  d->n_cols = h.n_cols;
+  d->nnz = static_cast<int64_t>(h.col.size());
+  d->max_row_nnz = 0;
+  for (int32_t r = 0; r < h.n_rows; ++r) d->max_row_nnz = std::max(d->max_row_nnz, h.rowptr[r + 1] - h.rowptr[r]);
+  cudaError_t e;
+  if ((e = upload(&d->rowptr, h.rowptr, st)) != cudaSuccess) return e;
+  if ((e = upload(&d->col, h.col, st)) != cudaSuccess) return e;
+  return upload(&d->val, h.val, st);
+}
+
+static cudaError_t upload_rb(dsw_rb* d, const HostRb& h, cudaStream_t st) {
+  d->R = h.R;
+  d->n_blocks = h.n_blocks;
+  d->max_union = h.max_union;
+  d->total_union = static_cast<int64_t>(h.ucol.size());
+  cudaError_t e;
+  if ((e = upload(&d->blkptr, h.blkptr, st)) != cudaSuccess) return e;
+  if ((e = upload(&d->ucol, h.ucol, st)) != cudaSuccess) return e;
+  return upload(&d->uval, h.uval, st);
+}
+
+static void free_csr(dsw_csr* c) {
+  cudaFree(c->rowptr);
+  cudaFree(c->col);
+  cudaFree(c->val);
+  *c = dsw_csr{};
+}
+static void free_rb(dsw_rb* r) {
+  cudaFree(r->blkptr);
+  cudaFree(r->ucol);
+  cudaFree(r->uval);
+  *r = dsw_rb{};
+}
+
+}  // namespace dsw
+
+using namespace dsw;
+
+extern "C" {
+
+int dsw_version(void) { return DSW_VERSION; }
+
+const char* dsw_strerror(int s) {
+  switch (s) {
+    case DSW_OK: return "success";
+    case DSW_ERR_BAD_ARGUMENT: return "bad argument (null pointer, non-positive size or bad enum)";
+    case DSW_ERR_SHAPE: return "shape mismatch between plan and tensors";
+    case DSW_ERR_WORKSPACE: return "workspace missing or too small";
+    case DSW_ERR_UNSUPPORTED: return "unsupported configuration";
+    case DSW_ERR_CUDA: return "CUDA runtime error (see dsw_last_cuda_error_string)";
+    case DSW_ERR_NO_DEVICE: return "no usable CUDA device (sm_100 required)";
+    case DSW_ERR_ALIGNMENT: return "pointer or stride alignment violated";
+    default: return "unknown dsw status";
+  }
+}
+
+int dsw_last_cuda_error(void) { return static_cast<int>(last_cuda_error()); }
+const char* dsw_last_cuda_error_string(void) { return cudaGetErrorString(last_cuda_error()); }
+
+int dsw_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int64_t dsw_launch_count(void) { return g_launches.load(); }
+int dsw_set_mix_mode(int mode) {
+  if (mode < 0 || mode > 1) return DSW_ERR_BAD_ARGUMENT;
+  g_mix_mode.store(mode);
+  return DSW_OK;
+}
+int dsw_get_mix_mode(void) { return g_mix_mode.load(); }
+
+int dsw_plan_create(int32_t n_rows, int32_t n_cols, int64_t nnz, const int64_t* coo_row,
+                    const int64_t* coo_col, const float* coo_val, void* stream, dsw_plan** out) {
+  if (!out) return DSW_ERR_BAD_ARGUMENT;
+  *out = nullptr;
+  if (n_rows <= 0 || n_cols <= 0 || nnz < 0) return DSW_ERR_BAD_ARGUMENT;
+  if (nnz > 0 && (!coo_row || !coo_col || !coo_val)) return DSW_ERR_BAD_ARGUMENT;
+  if (nnz > INT32_MAX) return DSW_ERR_UNSUPPORTED;
+  if (dsw_device_count() <= 0) return DSW_ERR_NO_DEVICE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  std::vector<int64_t> r(nnz), c(nnz);
+  std::vector<float> v(nnz);
+  if (nnz > 0) {
+    DSW_CUDA_TRY(cudaStreamSynchronize(st));
+    DSW_CUDA_TRY(cudaMemcpy(r.data(), coo_row, nnz * sizeof(int64_t), cudaMemcpyDefault));
+    DSW_CUDA_TRY(cudaMemcpy(c.data(), coo_col, nnz * sizeof(int64_t), cudaMemcpyDefault));
+    DSW_CUDA_TRY(cudaMemcpy(v.data(), coo_val, nnz * sizeof(float), cudaMemcpyDefault));
+  }
+  for (int64_t i = 0; i < nnz; ++i)
+    if (r[i] < 0 || r[i] >= n_rows || c[i] < 0 || c[i] >= n_cols) return DSW_ERR_SHAPE;
+
+  HostCsr fwd = build_csr(n_rows, n_cols, nnz, r.data(), c.data(), v.data());
+  HostCsr tr = transpose(fwd);
+
+  dsw_plan* p = new dsw_plan();
+  cudaError_t e = cudaGetDevice(&p->device);
+  if (e == cudaSuccess) e = upload_csr(&p->fwd, fwd, st);
+  if (e == cudaSuccess) e = upload_csr(&p->tr, tr, st);
+  if (e == cudaSuccess) {
+    const int32_t rf = pick_rb_rows(fwd);
+    if (rf > 0) e = upload_rb(&p->fwd_rb, build_rb(fwd, rf), st);
+  }
+  if (e == cudaSuccess) {
+    const int32_t rt = pick_rb_rows(tr);
+    if (rt > 0) e = upload_rb(&p->tr_rb, build_rb(tr, rt), st);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // host vectors go out of scope
+  if (e != cudaSuccess) {
+    set_cuda_error(e);
+    dsw_plan_destroy(p);
+    return DSW_ERR_CUDA;
+  }
+  *out = p;
+  return DSW_OK;
+}
+
+void dsw_plan_destroy(dsw_plan* p) {
+  if (!p) return;
+  free_csr(&p->fwd);
+  free_csr(&p->tr);
+  free_rb(&p->fwd_rb);
+  free_rb(&p->tr_rb);
+  delete p;
+}
+
+int dsw_plan_shape(const dsw_plan* p, int32_t* n_rows, int32_t* n_cols, int64_t* nnz, int32_t* max_row_nnz) {
+  if (!p) return DSW_ERR_BAD_ARGUMENT;
+  if (n_rows) *n_rows = p->fwd.n_rows;
+  if (n_cols) *n_cols = p->fwd.n_cols;
+  if (nnz) *nnz = p->fwd.nnz;
+  if (max_row_nnz) *max_row_nnz = p->fwd.max_row_nnz;
+  return DSW_OK;
+}
+
+int64_t dsw_plan_operand_bytes(const dsw_plan* p) {
+  if (!p) return 0;
+  return 8 * p->fwd.nnz + 4 * (static_cast<int64_t>(p->fwd.n_rows) + 1);
+}
+
+}  // extern "C"

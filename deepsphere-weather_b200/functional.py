@@ -1,0 +1,443 @@
+"""Autograd functions over the C-ABI (``libdsw.so``) — the host-side half of the hot path.
+
+Each ``torch.autograd.Function`` maps to one row of SURVEY.md §8a.  Tensors cross the boundary as
+raw device pointers + element strides; PyTorch only provides memory, streams and autograd
+bookkeeping.  Non-CUDA tensors raise (no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda_f32(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{name} must be a CUDA tensor: deepsphere_weather_b200 has no CPU path "
+            f"(got device {t.device})."
+        )
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32 (got {t.dtype})")
+
+
+def _channel_last(x: torch.Tensor) -> torch.Tensor:
+    """The kernels take arbitrary batch / node strides but need unit feature stride."""
+    if x.stride(2) != 1 and x.shape[2] != 1:
+        return x.contiguous()
+    if x.shape[2] == 1 and x.stride(2) != 1:
+        return x.contiguous()
+    return x
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------------------------
+# Plans
+# --------------------------------------------------------------------------------------------
+
+
+class SparsePlan:
+    """Device-resident CSR / CSR^T / row-block layouts of one sparse operator (``dsw_plan``).
+
+    Built from exactly what the reference stores in its module buffers: a coalesced
+    ``torch.sparse_coo_tensor`` with int64 indices and fp32 values (``layers.py:82-106,584-594``).
+    """
+
+    def __init__(self, coo: torch.Tensor):
+        if not coo.is_sparse:
+            raise TypeError("SparsePlan expects a torch sparse COO tensor")
+        if not coo.is_cuda:
+            raise RuntimeError("SparsePlan needs the sparse operator on a CUDA device (no CPU path)")
+        coo = coo.coalesce()
+        idx = coo.indices().contiguous()
+        val = coo.values().to(torch.float32).contiguous()
+        self.shape = tuple(coo.shape)
+        self.nnz = int(val.numel())
+        self.device = coo.device
+        lib = _lib.load()
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = lib.dsw_plan_create(
+                self.shape[0], self.shape[1], self.nnz, idx[0].data_ptr(), idx[1].data_ptr(), val.data_ptr(),
+                _stream_ptr(self.device), C.byref(handle),
+            )
+        _lib.check(rc, "dsw_plan_create")
+        self.handle = handle
+        self._finalizer = weakref.finalize(self, lib.dsw_plan_destroy, handle)
+
+    @property
+    def operand_bytes(self) -> int:
+        return int(_lib.load().dsw_plan_operand_bytes(self.handle))
+
+
+_PLAN_CACHE: dict = {}
+
+
+def plan_for(coo: torch.Tensor) -> SparsePlan:
+    """Plan cache keyed by operator content (modules of one U-Net level share a Laplacian but
+    ``module.to(device)`` gives each its own copy of the buffer)."""
+    if not coo.is_cuda:
+        raise RuntimeError("sparse operator must live on a CUDA device (no CPU path)")
+    ident = (coo.device.index, id(coo), coo._version if hasattr(coo, "_version") else 0)
+    hit = _PLAN_CACHE.get(ident)
+    if hit is not None and hit[0]() is coo:
+        return hit[1]
+    c = coo.coalesce()
+    vals, idx = c.values(), c.indices()
+    key = (
+        coo.device.index, tuple(coo.shape), int(vals.numel()),
+        float(vals.double().sum()), float((vals.double() * (idx[0] + 2 * idx[1] + 1)).sum()),
+    )
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        plan = SparsePlan(c)
+        _PLAN_CACHE[key] = plan
+    _PLAN_CACHE[ident] = (weakref.ref(coo), plan)
+    return plan
+
+
+# --------------------------------------------------------------------------------------------
+# Chebyshev convolution                                           reference layers.py:113-180, 365-376
+# --------------------------------------------------------------------------------------------
+
+
+class ChebConvFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, plan: SparsePlan):
+        _require_cuda_f32(x, "inputs")
+        _require_cuda_f32(weight, "weight")
+        B, V, Fin = x.shape
+        Fin_w, K, Fout = weight.shape
+        if Fin != Fin_w:  # same check and message as layers.py:149-154
+            raise ValueError(
+                "Input tensor shape does not match the expected shape: \n"
+                + "- Input tensor shape :{} \n".format(Fin)
+                + "- Expected tensor shape :{} \n".format(Fin_w)
+            )
+        if V != plan.shape[0]:
+            raise ValueError(f"inputs have {V} nodes but the laplacian is {plan.shape}")
+        lib = _lib.load()
+        x = _channel_last(x)
+        w = weight.contiguous()
+        bptr = None
+        if bias is not None:
+            _require_cuda_f32(bias, "bias")
+            bptr = bias.contiguous().data_ptr()
+        y = torch.empty((B, V, Fout), dtype=torch.float32, device=x.device)
+        ws = _workspace(lib.dsw_cheb_fwd_workspace_bytes(B, V, Fin, Fout, K), x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.dsw_cheb_fwd(
+                plan.handle, x.data_ptr(), x.stride(0), x.stride(1), w.data_ptr(), bptr, y.data_ptr(),
+                B, Fin, Fout, K, 0, ws.data_ptr(), ws.numel(), _stream_ptr(x.device),
+            )
+        _lib.check(rc, "dsw_cheb_fwd")
+        # Only x and W are saved: callers modify our output in place (`x_out *= rezero_weight`,
+        # my_models_graph.py:213), so the backward recomputes the Chebyshev terms instead.
+        ctx.save_for_backward(x, w)
+        ctx.plan = plan
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        plan = ctx.plan
+        lib = _lib.load()
+        B, V, Fin = x.shape
+        _, K, Fout = w.shape
+        dy = dy.contiguous()
+        dx = dw = db = None
+        st = _stream_ptr(x.device)
+        with torch.cuda.device(x.device):
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty((B, V, Fin), dtype=torch.float32, device=x.device)
+                ws = _workspace(lib.dsw_cheb_bwd_data_workspace_bytes(B, V, Fin, Fout, K), x.device)
+                rc = lib.dsw_cheb_bwd_data(
+                    plan.handle, dy.data_ptr(), w.data_ptr(), dx.data_ptr(), B, Fin, Fout, K,
+                    ws.data_ptr(), ws.numel(), st,
+                )
+                _lib.check(rc, "dsw_cheb_bwd_data")
+            if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+                dw = torch.empty_like(w)
+                db = torch.empty(Fout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+                ws = _workspace(lib.dsw_cheb_bwd_weight_workspace_bytes(B, V, Fin, Fout, K), x.device)
+                rc = lib.dsw_cheb_bwd_weight(
+                    plan.handle, x.data_ptr(), x.stride(0), x.stride(1), dy.data_ptr(), dw.data_ptr(),
+                    db.data_ptr() if db is not None else None, B, Fin, Fout, K,
+                    ws.data_ptr(), ws.numel(), st,
+                )
+                _lib.check(rc, "dsw_cheb_bwd_weight")
+        return dx, dw, db, None
+
+
+def cheb_conv(x, weight, bias, plan: SparsePlan):
+    return ChebConvFunction.apply(x, weight, bias, plan)
+
+
+def cheb_terms(x: torch.Tensor, plan: SparsePlan, K: int) -> torch.Tensor:
+    """The recurrence alone: ``[K-1, B, V, F]`` holding T_1 x .. T_{K-1} x (layers.py:163-169)."""
+    _require_cuda_f32(x, "inputs")
+    x = _channel_last(x)
+    B, V, F = x.shape
+    out = torch.empty((max(K - 1, 0), B, V, F), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().dsw_cheb_terms(
+            plan.handle, x.data_ptr(), x.stride(0), x.stride(1), out.data_ptr(), B, F, K, _stream_ptr(x.device)
+        )
+    _lib.check(rc, "dsw_cheb_terms")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# Sparse remap                                                     reference layers.py:956-964
+# --------------------------------------------------------------------------------------------
+
+
+class RemapFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, plan: SparsePlan):
+        _require_cuda_f32(x, "x")
+        B, V, F = x.shape
+        if V != plan.shape[1]:
+            raise ValueError(f"x has {V} nodes but remap_matrix is {plan.shape}")
+        x = _channel_last(x)
+        y = torch.empty((B, plan.shape[0], F), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.load().dsw_spmm_fwd(
+                plan.handle, x.data_ptr(), x.stride(0), x.stride(1), y.data_ptr(), B, F, _stream_ptr(x.device)
+            )
+        _lib.check(rc, "dsw_spmm_fwd")
+        ctx.plan = plan
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        plan = ctx.plan
+        dy = _channel_last(dy)
+        B, _, F = dy.shape
+        dx = torch.empty((B, plan.shape[1], F), dtype=torch.float32, device=dy.device)
+        with torch.cuda.device(dy.device):
+            rc = _lib.load().dsw_spmm_bwd(
+                plan.handle, dy.data_ptr(), dy.stride(0), dy.stride(1), dx.data_ptr(), B, F, _stream_ptr(dy.device)
+            )
+        _lib.check(rc, "dsw_spmm_bwd")
+        return dx, None
+
+
+def remap(x, plan: SparsePlan):
+    return RemapFunction.apply(x, plan)
+
+
+# --------------------------------------------------------------------------------------------
+# Max-value pooling with indices                                 reference layers.py:1040-1103
+# --------------------------------------------------------------------------------------------
+
+
+class MaxValPoolFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, plan: SparsePlan):
+        _require_cuda_f32(x, "x")
+        B, V, F = x.shape
+        assert V == plan.shape[1], "remap_matrix.shape[1] != x.shape[1]"  # layers.py:1048
+        Vc = plan.shape[0]
+        x = _channel_last(x)
+        y = torch.empty((B, Vc, F), dtype=torch.float32, device=x.device)
+        index = torch.empty((2, F * B * Vc), dtype=torch.int64, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.load().dsw_maxval_pool_fwd(
+                plan.handle, x.data_ptr(), x.stride(0), x.stride(1), y.data_ptr(),
+                index[0].data_ptr(), index[1].data_ptr(), B, F, _stream_ptr(x.device),
+            )
+        _lib.check(rc, "dsw_maxval_pool_fwd")
+        ctx.save_for_backward(index)
+        ctx.dims = (B, V, Vc, F)
+        ctx.mark_non_differentiable(index)
+        return y, index
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy, _dindex):
+        (index,) = ctx.saved_tensors
+        B, V, Vc, F = ctx.dims
+        dy = dy.contiguous()
+        dx = torch.empty((B, V, F), dtype=torch.float32, device=dy.device)
+        with torch.cuda.device(dy.device):
+            rc = _lib.load().dsw_maxval_pool_bwd(
+                dy.data_ptr(), index[0].data_ptr(), dx.data_ptr(), B, V, Vc, F, _stream_ptr(dy.device)
+            )
+        _lib.check(rc, "dsw_maxval_pool_bwd")
+        return dx, None
+
+
+class ScatterUnpoolFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, index, n_fine: int):
+        _require_cuda_f32(x, "x")
+        B, Vc, F = x.shape
+        if index.dtype != torch.int64 or index.shape != (2, F * B * Vc):
+            raise ValueError("index must be the int64 [2, F*B*Vc] tensor returned by the max-value pool")
+        x = x.contiguous()
+        index = index.contiguous()
+        out = torch.empty((B, n_fine, F), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.load().dsw_scatter_unpool_fwd(
+                x.data_ptr(), index[0].data_ptr(), index[1].data_ptr(), out.data_ptr(), B, n_fine, Vc, F,
+                _stream_ptr(x.device),
+            )
+        _lib.check(rc, "dsw_scatter_unpool_fwd")
+        ctx.save_for_backward(index)
+        ctx.dims = (B, n_fine, Vc, F)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        (index,) = ctx.saved_tensors
+        B, V, Vc, F = ctx.dims
+        dout = dout.contiguous()
+        dx = torch.empty((B, Vc, F), dtype=torch.float32, device=dout.device)
+        with torch.cuda.device(dout.device):
+            rc = _lib.load().dsw_scatter_unpool_bwd(
+                dout.data_ptr(), index[0].data_ptr(), index[1].data_ptr(), dx.data_ptr(), B, V, Vc, F,
+                _stream_ptr(dout.device),
+            )
+        _lib.check(rc, "dsw_scatter_unpool_bwd")
+        return dx, None, None
+
+
+# --------------------------------------------------------------------------------------------
+# Nested-order pools                                               reference layers.py:784-941
+# --------------------------------------------------------------------------------------------
+
+
+class NestedMaxPoolFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kernel: int):
+        _require_cuda_f32(x, "x")
+        B, V, F = x.shape
+        x = _channel_last(x)
+        Vc = V // kernel
+        y = torch.empty((B, Vc, F), dtype=torch.float32, device=x.device)
+        idx = torch.empty((B, F, Vc), dtype=torch.int64, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.load().dsw_nested_maxpool_fwd(
+                x.data_ptr(), x.stride(0), x.stride(1), y.data_ptr(), idx.data_ptr(), B, V, F, kernel,
+                _stream_ptr(x.device),
+            )
+        _lib.check(rc, "dsw_nested_maxpool_fwd")
+        ctx.save_for_backward(idx)
+        ctx.dims = (B, V, F, kernel)
+        ctx.mark_non_differentiable(idx)
+        return y, idx
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy, _didx):
+        (idx,) = ctx.saved_tensors
+        B, V, F, kernel = ctx.dims
+        dy = dy.contiguous()
+        dx = torch.empty((B, V, F), dtype=torch.float32, device=dy.device)
+        with torch.cuda.device(dy.device):
+            rc = _lib.load().dsw_nested_scatter(dy.data_ptr(), idx.data_ptr(), dx.data_ptr(), B, V, F, kernel,
+                                               _stream_ptr(dy.device))
+        _lib.check(rc, "dsw_nested_scatter")
+        return dx, None
+
+
+class NestedMaxUnpoolFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, idx, kernel: int):
+        _require_cuda_f32(x, "x")
+        B, Vc, F = x.shape
+        V = Vc * kernel
+        x = x.contiguous()
+        idx = idx.contiguous()
+        out = torch.empty((B, V, F), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.load().dsw_nested_scatter(x.data_ptr(), idx.data_ptr(), out.data_ptr(), B, V, F, kernel,
+                                               _stream_ptr(x.device))
+        _lib.check(rc, "dsw_nested_scatter")
+        ctx.save_for_backward(idx)
+        ctx.dims = (B, V, F, kernel)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        (idx,) = ctx.saved_tensors
+        B, V, F, kernel = ctx.dims
+        dout = dout.contiguous()
+        dx = torch.empty((B, V // kernel, F), dtype=torch.float32, device=dout.device)
+        with torch.cuda.device(dout.device):
+            rc = _lib.load().dsw_nested_gather(dout.data_ptr(), idx.data_ptr(), dx.data_ptr(), B, V, F, kernel,
+                                              _stream_ptr(dout.device))
+        _lib.check(rc, "dsw_nested_gather")
+        return dx, None, None
+
+
+class NestedAvgPoolFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kernel: int):
+        _require_cuda_f32(x, "x")
+        B, V, F = x.shape
+        x = _channel_last(x)
+        y = torch.empty((B, V // kernel, F), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.load().dsw_nested_avgpool_fwd(x.data_ptr(), x.stride(0), x.stride(1), y.data_ptr(), B, V, F,
+                                                   kernel, _stream_ptr(x.device))
+        _lib.check(rc, "dsw_nested_avgpool_fwd")
+        ctx.dims = (B, V, F, kernel)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        B, V, F, kernel = ctx.dims
+        dy = _channel_last(dy)
+        dx = torch.empty((B, V, F), dtype=torch.float32, device=dy.device)
+        with torch.cuda.device(dy.device):
+            rc = _lib.load().dsw_nested_repeat(dy.data_ptr(), dy.stride(0), dy.stride(1), dx.data_ptr(),
+                                              1.0 / kernel, B, V, F, kernel, _stream_ptr(dy.device))
+        _lib.check(rc, "dsw_nested_repeat")
+        return dx, None
+
+
+class NestedAvgUnpoolFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kernel: int):
+        _require_cuda_f32(x, "x")
+        B, Vc, F = x.shape
+        x = _channel_last(x)
+        V = Vc * kernel
+        y = torch.empty((B, V, F), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.load().dsw_nested_repeat(x.data_ptr(), x.stride(0), x.stride(1), y.data_ptr(), 1.0, B, V, F,
+                                              kernel, _stream_ptr(x.device))
+        _lib.check(rc, "dsw_nested_repeat")
+        ctx.dims = (B, V, F, kernel)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        B, V, F, kernel = ctx.dims
+        dy = _channel_last(dy)
+        dx = torch.empty((B, V // kernel, F), dtype=torch.float32, device=dy.device)
+        with torch.cuda.device(dy.device):
+            rc = _lib.load().dsw_nested_sum(dy.data_ptr(), dy.stride(0), dy.stride(1), dx.data_ptr(), B, V, F,
+                                           kernel, _stream_ptr(dy.device))
+        _lib.check(rc, "dsw_nested_sum")
+        return dx, None

@@ -1,0 +1,298 @@
+"""Drop-in layers with the reference's L2 interface (``modules/layers.py`` of
+deepsphere/deepsphere-weather), computing through ``libdsw.so``.
+
+Same class names, constructor signatures, attributes, buffers and state-dict keys as the
+reference, so ``my_models_graph.py`` / ``models.py`` run on them unchanged (INTEGRATION.md shows
+the one-line rebinding).  Differences by design:
+
+* there is no CPU path — CUDA tensors only;
+* pool / unpool outputs are contiguous ``[B, V', F]`` (the reference returns a strided view of a
+  ``[V', F, B]`` buffer, ``layers.py:963``); values are identical;
+* sparse operators are turned into device plans lazily on the first forward after ``.to(device)``
+  and are *not* part of the state dict.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+from scipy import sparse
+
+from . import functional as F_
+from .graphs import prepare_torch_laplacian, scipy_to_torch_coo  # noqa: F401  (re-export)
+
+_RELU_LIKE = {
+    "relu", "celu", "selu", "prelu", "hardswish", "mish", "silu", "gelu", "softplus", "softmax",
+    "logsigmoid", "relu6", "rrlu", "leaky_relu", "elu",
+}
+_LINEAR_LIKE = {"linear", "hardshrink ", "sigmoid", "hardsigmoid", "tanh", "hardtanh", "softsign"}
+
+
+def convert_to_torch_sparse(mat) -> torch.Tensor:
+    """scipy sparse -> coalesced torch COO (reference ``layers.py:584-594``)."""
+    return scipy_to_torch_coo(mat, torch.get_default_dtype())
+
+
+# ------------------------------------------------------------------------------------------
+# Chebyshev graph convolution
+# ------------------------------------------------------------------------------------------
+
+
+def conv_cheb(laplacian: torch.Tensor, inputs: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """Functional form with the reference's signature (``layers.py:113``)."""
+    return F_.cheb_conv(inputs, weight, None, F_.plan_for(laplacian))
+
+
+class ConvCheb(torch.nn.Module):
+    """Graph convolution by Chebyshev polynomials of the Laplacian (reference ``layers.py:183-376``).
+
+    ``forward(inputs[B, V, Fin]) -> [B, V, Fout]``; parameters ``weight[Fin, K, Fout]``,
+    ``bias[Fout]`` (or ``None``); buffer ``laplacian`` (sparse COO, persistent — checkpoints of the
+    reference load with ``strict=True``).  Recurrence, channel mix and bias run as one library call.
+    """
+
+    def __init__(self, in_channels, out_channels, kernel_size, laplacian, bias=True, conv=conv_cheb, **kwargs):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = kernel_size
+        self._conv = conv
+        self.register_buffer("laplacian", laplacian)
+        self.weight = torch.nn.Parameter(torch.empty(in_channels, kernel_size, out_channels))
+        if bias:
+            self.bias = torch.nn.Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self, activation="relu", fan="in", distribution="normal"):
+        """He / Glorot / LeCun initialisation, same options as the reference (``layers.py:253-343``)."""
+        k = self.kernel_size
+        if fan == "in":
+            fan_v = self.in_channels * k
+        elif fan == "out":
+            fan_v = self.out_channels * k
+        elif fan == "avg":
+            fan_v = (self.in_channels + self.out_channels) / 2 * k
+        else:
+            raise ValueError("unknown fan")
+        if activation in _RELU_LIKE:
+            gain = 2
+        elif activation in _LINEAR_LIKE:
+            gain = 1
+        else:
+            raise ValueError("Unknown activation")
+        with torch.no_grad():
+            if distribution == "normal":
+                self.weight.normal_(0, math.sqrt(gain / fan_v))
+            elif distribution == "uniform":
+                lim = math.sqrt(3 * gain / fan_v)
+                self.weight.uniform_(-lim, lim)
+            else:
+                raise ValueError("Unknown distribution")
+            if self.bias is not None:
+                self.bias.fill_(0)
+
+    def set_parameters(self, weight, bias=None):
+        self.weight = torch.nn.Parameter(torch.as_tensor(weight))
+        if bias is not None:
+            self.bias = torch.nn.Parameter(torch.as_tensor(bias))
+
+    def extra_repr(self):
+        return "{} -> {}, kernel_size={}, bias={}".format(
+            self.in_channels, self.out_channels, self.kernel_size, self.bias is not None
+        )
+
+    def forward(self, inputs):
+        if self._conv is not conv_cheb:  # user-supplied convolution: honour the reference contract
+            out = self._conv(self.laplacian, inputs, self.weight)
+            if self.bias is not None:
+                out += self.bias
+            return out
+        return F_.cheb_conv(inputs, self.weight, self.bias, F_.plan_for(self.laplacian))
+
+
+# ------------------------------------------------------------------------------------------
+# Nested-order (HEALPix) pools                                    reference layers.py:784-941
+# ------------------------------------------------------------------------------------------
+
+
+class HealpixMaxPool(torch.nn.Module):
+    def __init__(self, kernel_size, return_indices=True, *args, **kwargs):
+        super().__init__()
+        self.kernel_size = kernel_size
+        self.return_indices = return_indices
+
+    def extra_repr(self):
+        return f"kernel_size={self.kernel_size}"
+
+    def forward(self, x):
+        y, idx = F_.NestedMaxPoolFunction.apply(x, self.kernel_size)
+        return (y, idx) if self.return_indices else y
+
+
+class HealpixMaxUnpool(torch.nn.Module):
+    def __init__(self, kernel_size, *args, **kwargs):
+        super().__init__()
+        self.kernel_size = kernel_size
+
+    def extra_repr(self):
+        return f"kernel_size={self.kernel_size}"
+
+    def forward(self, x, indices, **kwargs):
+        return F_.NestedMaxUnpoolFunction.apply(x, indices, self.kernel_size)
+
+
+class HealpixAvgPool(torch.nn.Module):
+    def __init__(self, kernel_size, *args, **kwargs):
+        super().__init__()
+        self.kernel_size = kernel_size
+
+    def extra_repr(self):
+        return f"kernel_size={self.kernel_size}"
+
+    def forward(self, x):
+        return F_.NestedAvgPoolFunction.apply(x, self.kernel_size), None
+
+
+class HealpixAvgUnpool(torch.nn.Module):
+    def __init__(self, kernel_size, *args, **kwargs):
+        super().__init__()
+        self.kernel_size = kernel_size
+
+    def extra_repr(self):
+        return f"kernel_size={self.kernel_size}"
+
+    def forward(self, x, *args):
+        return F_.NestedAvgUnpoolFunction.apply(x, self.kernel_size)
+
+
+# ------------------------------------------------------------------------------------------
+# Remap-matrix pools                                             reference layers.py:948-1103
+# ------------------------------------------------------------------------------------------
+
+
+class RemapBlock(torch.nn.Module):
+    """``out[b, v', f] = sum_v M[v', v] x[b, v, f]`` with ``M`` the ``remap_matrix`` buffer."""
+
+    def __init__(self, remap_matrix):
+        super().__init__()
+        self.register_buffer("remap_matrix", self.process_remap_matrix(remap_matrix))
+
+    def process_remap_matrix(self, mat):
+        return convert_to_torch_sparse(mat)
+
+    def forward(self, x, *args, **kwargs):
+        return F_.remap(x, F_.plan_for(self.remap_matrix))
+
+
+class GeneralAvgPool(RemapBlock):
+    def forward(self, x, *args, **kwargs):
+        return super().forward(x), None
+
+
+class GeneralAvgUnpool(RemapBlock):
+    def forward(self, x, *args, **kwargs):
+        return super().forward(x)
+
+
+def _one_hot_coo(rows, cols, shape) -> torch.Tensor:
+    idx = torch.from_numpy(np.stack([np.asarray(rows, dtype=np.int64), np.asarray(cols, dtype=np.int64)]))
+    return torch.sparse_coo_tensor(
+        idx, torch.ones(idx.shape[1]), tuple(shape), dtype=torch.get_default_dtype(), check_invariants=False
+    ).coalesce()
+
+
+class GeneralMaxAreaPool(RemapBlock):
+    """Each coarse node copies the fine node with which it shares the largest area
+    (reference ``layers.py:991-1015``)."""
+
+    def forward(self, x, *args, **kwargs):
+        return super().forward(x), None
+
+    def process_remap_matrix(self, mat):
+        m = sparse.csr_matrix(mat)
+        winners = np.asarray(m.argmax(axis=1)).ravel()
+        return _one_hot_coo(np.arange(m.shape[0]), winners, m.shape)
+
+
+class GeneralMaxAreaUnpool(RemapBlock):
+    """Takes ``pool.T`` (fine x coarse); each coarse node writes to the single fine node holding
+    its column maximum (reference ``layers.py:1018-1036``)."""
+
+    def process_remap_matrix(self, mat):
+        m = sparse.csc_matrix(mat)
+        winners = np.asarray(m.argmax(axis=0)).ravel()
+        return _one_hot_coo(winners, np.arange(m.shape[1]), m.shape)
+
+
+class GeneralMaxValPool(RemapBlock):
+    """Per coarse node and channel, keep the fine value whose *weighted* value is largest; also
+    returns the reference's ``nnz_ind`` index tensor (``layers.py:1040-1083``)."""
+
+    def forward(self, x, *args, **kwargs):
+        return F_.MaxValPoolFunction.apply(x, F_.plan_for(self.remap_matrix))
+
+
+class GeneralMaxValUnpool(RemapBlock):
+    """Scatter pooled values back to the fine nodes they came from (``layers.py:1086-1103``)."""
+
+    def forward(self, x, index, *args, **kwargs):
+        return F_.ScatterUnpoolFunction.apply(x, index, self.remap_matrix.shape[0])
+
+
+# ------------------------------------------------------------------------------------------
+# Factories                                                       reference layers.py:1139-1242
+# ------------------------------------------------------------------------------------------
+
+HEALPIX_POOL = {"max": (HealpixMaxPool, HealpixMaxUnpool), "avg": (HealpixAvgPool, HealpixAvgUnpool)}
+ALL_POOL = {"healpix": HEALPIX_POOL}
+
+
+class PoolUnpoolBlock(torch.nn.Module):
+    @staticmethod
+    def getPoolUnpoolLayer(sampling: str, pool_method: str, **kwargs):
+        sampling, pool_method = sampling.lower(), pool_method.lower()
+        if sampling not in ALL_POOL:
+            raise NotImplementedError(
+                f"index pools for sampling '{sampling}' are outside the graph hot path (SURVEY.md §8f rank 4)"
+            )
+        assert pool_method in ("max", "avg")
+        pool, unpool = ALL_POOL[sampling][pool_method]
+        return pool(**kwargs), unpool(**kwargs)
+
+    @staticmethod
+    def getGeneralPoolUnpoolLayer(src_graph=None, dst_graph=None, pool_method: str = "interp", matrices=None):
+        """``matrices = (pool_mat, unpool_mat)`` as scipy sparse: the reference computes them with
+        xsphere/CDO (``layers.py:576-581``), which is an input to — not part of — the hot path."""
+        if matrices is None:
+            raise NotImplementedError("conservative-remap weights come from xsphere/CDO; pass matrices=(pool, unpool)")
+        pool_mat, unpool_mat = matrices
+        if pool_method == "interp":
+            return GeneralAvgPool(pool_mat), GeneralAvgUnpool(unpool_mat)
+        if pool_method == "maxarea":
+            return GeneralMaxAreaPool(pool_mat), GeneralMaxAreaUnpool(sparse.coo_matrix(pool_mat).T)
+        if pool_method == "maxval":
+            return GeneralMaxValPool(pool_mat), GeneralMaxValUnpool(unpool_mat)
+        if pool_method == "learn":
+            raise NotImplementedError()
+        raise ValueError(f"{pool_method} is not supoorted.")
+
+
+def get_conv_fun(conv_type):
+    if conv_type != "graph":
+        raise NotImplementedError("only the graph convolution is on the B200 hot path")
+    return ConvCheb
+
+
+class GeneralConvBlock(torch.nn.Module):
+    @staticmethod
+    def getConvLayer(in_channels: int, out_channels: int, kernel_size: int, conv_type: str = "graph", **kwargs):
+        conv_type = conv_type.lower()
+        if conv_type != "graph":
+            raise ValueError("{} conv_type is not supported. Choose 'graph'".format(conv_type))
+        assert "laplacian" in kwargs
+        kwargs.pop("lonlat_ratio", None)
+        kwargs.pop("periodic_padding", None)
+        return ConvCheb(in_channels, out_channels, kernel_size, **kwargs)

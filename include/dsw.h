@@ -1,0 +1,181 @@
+/*
+ * dsw.h — C-ABI of libdsw.so: the B200 (sm_100a) implementation of DeepSphere-Weather's
+ * spherical graph-convolution hot path.
+ *
+ * The reference (deepsphere/deepsphere-weather) is pure Python: it has no FFI seam, the seam is
+ * Python class identity in modules/layers.py.  This header is therefore the
+ * interface a ctypes binding inside modules/layers.py would load (INTEGRATION.md shows that
+ * binding); every entry point names the reference lines it replaces (paths relative to the
+ * reference root).
+ *
+ * Conventions
+ *  - plain C types only; no torch / C++ types cross this boundary;
+ *  - every data pointer is a DEVICE pointer on the current CUDA device unless stated otherwise;
+ *  - `stream` is a cudaStream_t passed as void*; every kernel is launched on it, nothing syncs
+ *    except dsw_plan_create (one-time setup);
+ *  - the caller owns all tensors, outputs and workspaces; the library owns only dsw_plan
+ *    internals.  No allocation happens on the hot path;
+ *  - node features are fp32, channel-last: x[b][v][f] at x + b*sB + v*sV + f (element strides,
+ *    feature stride 1).  Outputs are written densely ([B][V][F] contiguous);
+ *  - return value: 0 on success, a negative dsw_status otherwise; dsw_strerror() names it.
+ *  - re-entrant: no global mutable state; plans are immutable after creation.
+ */
+#ifndef DSW_H_
+#define DSW_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSW_VERSION 100 /* major*100 + minor */
+
+typedef enum dsw_status {
+  DSW_OK = 0,
+  DSW_ERR_BAD_ARGUMENT = -1,  /* null pointer, non-positive size, bad enum */
+  DSW_ERR_SHAPE = -2,         /* shapes inconsistent with the plan / each other */
+  DSW_ERR_WORKSPACE = -3,     /* workspace pointer null or too small */
+  DSW_ERR_UNSUPPORTED = -4,   /* e.g. kernel_size > DSW_MAX_K */
+  DSW_ERR_CUDA = -5,          /* a CUDA runtime call or launch failed (see dsw_last_cuda_error) */
+  DSW_ERR_NO_DEVICE = -6,     /* no CUDA device / wrong architecture (needs sm_100) */
+  DSW_ERR_ALIGNMENT = -7      /* pointer / stride alignment required by the fast path violated */
+} dsw_status;
+
+#define DSW_MAX_K 16
+
+/* Opaque sparse-operator plan: CSR (int32) of the operator and of its transpose, plus the
+ * row-block layouts the kernels use.  Built once per Laplacian / remap matrix. */
+typedef struct dsw_plan dsw_plan;
+
+int dsw_version(void);
+const char* dsw_strerror(int status);
+/* Last cudaError_t (as int) recorded by a failing call on this thread, and its string. */
+int dsw_last_cuda_error(void);
+const char* dsw_last_cuda_error_string(void);
+
+/* Number of CUDA devices visible (0 without a GPU; never fails). */
+int dsw_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Plans.  Replaces the per-call COO->CSR conversion hidden inside torch.sparse.mm
+ * (modules/layers.py:164,167,962) and consumes exactly what prepare_torch_laplacian
+ * (layers.py:82-106) / convert_to_torch_sparse (layers.py:584-594) produce: a coalesced COO
+ * matrix with int64 indices and fp32 values.  coo_row / coo_col / coo_val may be host or device
+ * pointers.  Duplicates are summed; entries need not be sorted.
+ * ------------------------------------------------------------------------------------------- */
+int dsw_plan_create(int32_t n_rows, int32_t n_cols, int64_t nnz, const int64_t* coo_row,
+                    const int64_t* coo_col, const float* coo_val, void* stream, dsw_plan** out);
+void dsw_plan_destroy(dsw_plan* plan);
+int dsw_plan_shape(const dsw_plan* plan, int32_t* n_rows, int32_t* n_cols, int64_t* nnz,
+                   int32_t* max_row_nnz);
+/* Bytes of the sparse operand one pass reads: 8*nnz + 4*(n_rows+1)  (BASELINE.md §4 "nnzB"). */
+int64_t dsw_plan_operand_bytes(const dsw_plan* plan);
+
+/* ---------------------------------------------------------------------------------------------
+ * Chebyshev graph convolution.  Replaces conv_cheb (modules/layers.py:113-180) + the bias add of
+ * ConvCheb.forward (layers.py:365-376):
+ *     y[b,v,:] = bias + sum_{k<K} (T_k(L) x_b)[v,:] . W[:,k,:],   T_0=I, T_1=L, T_k=2 L T_{k-1}-T_{k-2}
+ * W is the reference's parameter layout [Fin][K][Fout] contiguous; bias [Fout] or NULL.
+ * act: 0 = none, 1 = ReLU applied after the bias (ConvBlock.forward, my_models_graph.py:104-118).
+ * Workspace holds the K-1 intermediate Chebyshev terms.
+ * ------------------------------------------------------------------------------------------- */
+size_t dsw_cheb_fwd_workspace_bytes(int32_t B, int32_t V, int32_t Fin, int32_t Fout, int32_t K);
+int dsw_cheb_fwd(const dsw_plan* lap, const float* x, int64_t x_sB, int64_t x_sV, const float* W,
+                 const float* bias, float* y, int32_t B, int32_t Fin, int32_t Fout, int32_t K,
+                 int32_t act, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Only the recurrence: terms[k][b][v][f] for k = 1..K-1 written to `terms` ([K-1][B][V][F]
+ * contiguous); term 0 is x itself.  This is the "ChebConv SpMM" stage of BASELINE.json's metric
+ * (layers.py:163-169). */
+int dsw_cheb_terms(const dsw_plan* lap, const float* x, int64_t x_sB, int64_t x_sV, float* terms,
+                   int32_t B, int32_t F, int32_t K, void* stream);
+
+/* Gradient w.r.t. the input (autograd of layers.py:158-177 w.r.t. `inputs`):
+ *     dx_b = sum_k T_k(L^T) (dy_b . W[:,k,:]^T)        evaluated by the adjoint (Clenshaw) recurrence.
+ * dy is [B][V][Fout] contiguous, dx is written [B][V][Fin] contiguous. */
+size_t dsw_cheb_bwd_data_workspace_bytes(int32_t B, int32_t V, int32_t Fin, int32_t Fout, int32_t K);
+int dsw_cheb_bwd_data(const dsw_plan* lap, const float* dy, const float* W, float* dx, int32_t B,
+                      int32_t Fin, int32_t Fout, int32_t K, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* Gradient w.r.t. weight and bias (autograd of layers.py:176-177 and :375):
+ *     dW[f,k,o] = sum_{b,v} (T_k(L) x_b)[v,f] dy[b,v,o],   dbias[o] = sum_{b,v} dy[b,v,o]
+ * The Chebyshev terms are recomputed (they are not saved by the forward).  dW is overwritten
+ * ([Fin][K][Fout]); dbias may be NULL.  Deterministic (fixed-order two-pass reduction). */
+size_t dsw_cheb_bwd_weight_workspace_bytes(int32_t B, int32_t V, int32_t Fin, int32_t Fout, int32_t K);
+int dsw_cheb_bwd_weight(const dsw_plan* lap, const float* x, int64_t x_sB, int64_t x_sV,
+                        const float* dy, float* dW, float* dbias, int32_t B, int32_t Fin,
+                        int32_t Fout, int32_t K, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sparse remap (interpolation pooling / unpooling).  Replaces RemapBlock.forward
+ * (modules/layers.py:956-964) and its autograd:
+ *     fwd: y[b,r,:]  = sum_c M[r,c] x[b,c,:]        x [B][n_cols][F] (strided), y [B][n_rows][F]
+ *     bwd: dx[b,c,:] = sum_r M[r,c] dy[b,r,:]       dy [B][n_rows][F], dx [B][n_cols][F]
+ * ------------------------------------------------------------------------------------------- */
+int dsw_spmm_fwd(const dsw_plan* mat, const float* x, int64_t x_sB, int64_t x_sV, float* y,
+                 int32_t B, int32_t F, void* stream);
+int dsw_spmm_bwd(const dsw_plan* mat, const float* dy, int64_t dy_sB, int64_t dy_sV, float* dx,
+                 int32_t B, int32_t F, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Max-value pooling with index output.  Replaces GeneralMaxValPool.forward
+ * (modules/layers.py:1043-1083): for coarse row r and column c = f*B + b pick the stored entry j
+ * of row r maximising M[r,j]*x[b,j,f] (first maximum wins; NaN counts as maximum, as
+ * torch.argmax), output the unweighted x[b,j,f] and the reference's index tensor
+ * nnz_ind = int64[2][F*B*Vc]: idx_row[c*Vc + r] = j, idx_col[c*Vc + r] = c.   Bit-exact.
+ * bwd = the scatter-add that autograd derives from the final torch.gather (layers.py:1073).
+ * ------------------------------------------------------------------------------------------- */
+int dsw_maxval_pool_fwd(const dsw_plan* mat, const float* x, int64_t x_sB, int64_t x_sV, float* y,
+                        int64_t* idx_row, int64_t* idx_col, int32_t B, int32_t F, void* stream);
+int dsw_maxval_pool_bwd(const float* dy, const int64_t* idx_row, float* dx, int32_t B, int32_t V,
+                        int32_t Vc, int32_t F, void* stream);
+
+/* Replaces GeneralMaxValUnpool.forward (layers.py:1089-1103): out = zeros[B][V][F];
+ * out[b, idx_row[i], f] = x[b, r, f] with i = (f*B+b)*Vc + r and idx_col[i] decoding (f,b).
+ * bwd gathers dout at the same positions. */
+int dsw_scatter_unpool_fwd(const float* x, const int64_t* idx_row, const int64_t* idx_col,
+                           float* out, int32_t B, int32_t V, int32_t Vc, int32_t F, void* stream);
+int dsw_scatter_unpool_bwd(const float* dout, const int64_t* idx_row, const int64_t* idx_col,
+                           float* dx, int32_t B, int32_t V, int32_t Vc, int32_t F, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Nested-order (HEALPix) pools, window = stride = `kernel` consecutive nodes.  Replace
+ * HealpixMaxPool/MaxUnpool (layers.py:784-863) and HealpixAvgPool/AvgUnpool (layers.py:866-941).
+ * Max-pool indices are int64 [B][F][V/kernel] holding the fine node position (what
+ * F.max_pool1d(return_indices=True) returns on the [B,F,V] view).  Bit-exact.
+ * ------------------------------------------------------------------------------------------- */
+int dsw_nested_maxpool_fwd(const float* x, int64_t x_sB, int64_t x_sV, float* y, int64_t* idx,
+                           int32_t B, int32_t V, int32_t F, int32_t kernel, void* stream);
+/* dx[b, idx[b,f,r], f] = dy[b,r,f], zero elsewhere (also the forward of max-unpool). */
+int dsw_nested_scatter(const float* src, const int64_t* idx, float* dst, int32_t B, int32_t V,
+                       int32_t F, int32_t kernel, void* stream);
+/* dst[b,r,f] = src[b, idx[b,f,r], f] (backward of max-unpool). */
+int dsw_nested_gather(const float* src, const int64_t* idx, float* dst, int32_t B, int32_t V,
+                      int32_t F, int32_t kernel, void* stream);
+int dsw_nested_avgpool_fwd(const float* x, int64_t x_sB, int64_t x_sV, float* y, int32_t B,
+                           int32_t V, int32_t F, int32_t kernel, void* stream);
+/* y[b,v,f] = scale * x[b, v/kernel, f]: scale=1 is avg-unpool fwd (nearest repeat);
+ * scale=1/kernel is avg-pool bwd. */
+int dsw_nested_repeat(const float* x, int64_t x_sB, int64_t x_sV, float* y, float scale, int32_t B,
+                      int32_t V, int32_t F, int32_t kernel, void* stream);
+/* y[b,r,f] = sum_{i<kernel} x[b, r*kernel+i, f]  (avg-unpool bwd). */
+int dsw_nested_sum(const float* x, int64_t x_sB, int64_t x_sV, float* y, int32_t B, int32_t V,
+                   int32_t F, int32_t kernel, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Introspection used by bench.py / tests.
+ * ------------------------------------------------------------------------------------------- */
+/* Number of kernels launched by this library since process start (all threads). */
+int64_t dsw_launch_count(void);
+/* 0 = fp32 CUDA-core channel mix, 1 = tcgen05 split-bf16 (3-term) channel mix when shapes allow. */
+int dsw_set_mix_mode(int mode);
+int dsw_get_mix_mode(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSW_H_ */
