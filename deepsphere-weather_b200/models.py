@@ -259,3 +259,26 @@ def default_tensor_info(n_nodes: int, input_n_feature: int = 7, output_n_feature
         "input_shape_info": {"dynamic": {"node": n_nodes}},
         "output_shape_info": {"dynamic": {"node": n_nodes}},
     }
+
+
+def deterministic_fill(model: torch.nn.Module, seed: int = 0, rezero: float = 1.0) -> None:
+    """Deterministic, torch-version-independent parameter fill used by benchmarks and parity
+    harnesses: one numpy PCG64 stream per parameter name (He-normal for ConvCheb weights,
+    1/sqrt(fan_in) for the linear skips, N(0, 0.1) biases); every ``rezero_weight`` /
+    ``res_increment`` is set to ``rezero`` — they initialise to 0 (``my_models_graph.py:193``),
+    which would switch every convolution branch off."""
+    import zlib
+
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith("rezero_weight") or name.endswith("res_increment"):
+                p.fill_(rezero)
+                continue
+            rng = np.random.default_rng([seed, zlib.crc32(name.encode())])
+            if p.dim() == 3:  # ConvCheb weight [Fin, K, Fout]
+                std = float(np.sqrt(2.0 / (p.shape[0] * p.shape[1])))
+            elif p.dim() == 2:  # Linear skip [out, in]
+                std = 1.0 / np.sqrt(p.shape[1])
+            else:
+                std = 0.1
+            p.copy_(torch.from_numpy((rng.standard_normal(tuple(p.shape)) * std).astype(np.float32)))

@@ -73,21 +73,8 @@ def build_unet_oracle(*args, **kwargs):
 
 
 def fill_parameters(model: torch.nn.Module, seed: int = 0, rezero: float = 1.0) -> None:
-    """Deterministic, torch-version-independent parameter fill shared by every parity harness:
-    numpy PCG64 stream per parameter name; every ``rezero_weight`` / ``res_increment`` is set to
-    ``rezero`` (they initialise to 0, which would switch the conv branches off — SURVEY.md §7)."""
-    import zlib
+    """Deterministic parameter fill shared by every parity harness (see
+    ``deepsphere_weather_b200.models.deterministic_fill``)."""
+    from deepsphere_weather_b200.models import deterministic_fill
 
-    with torch.no_grad():
-        for name, p in model.named_parameters():
-            if name.endswith("rezero_weight") or name.endswith("res_increment"):
-                p.fill_(rezero)
-                continue
-            rng = np.random.default_rng([seed, zlib.crc32(name.encode())])
-            if p.dim() == 3:      # ConvCheb weight [Fin, K, Fout]
-                std = O.he_normal_std(p.shape[0], p.shape[1])
-            elif p.dim() == 2:    # Linear skip [out, in]
-                std = 1.0 / np.sqrt(p.shape[1])
-            else:                 # biases
-                std = 0.1
-            p.copy_(torch.from_numpy((rng.standard_normal(tuple(p.shape)) * std).astype(np.float32)))
+    deterministic_fill(model, seed, rezero)

@@ -1,0 +1,363 @@
+"""GPU parity tests (run with ``-m gpu`` on the B200 box): the CUDA path, called through the
+C-ABI, against (a) the golden vectors made by the unmodified reference and (b) the CPU oracle on
+seeded inputs; plus size-independent properties at BASELINE.json's full sizes.
+
+Tolerance (north_star): 1e-4 relative for fp32 values; integer / index outputs bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+from scipy import sparse
+
+from _util import CONV_CASES, REL_TOL, UNET_CASES, coo_from, golden, rel_err, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev(lib):
+    if not torch.cuda.is_available():
+        pytest.fail("CUDA device required for -m gpu tests (there is no CPU fallback)")
+    assert lib.dsw_device_count() > 0
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(params=[0, 1], ids=["mix-fp32", "mix-tcgen05"])
+def mix_mode(request, lib):
+    prev = lib.dsw_get_mix_mode()
+    assert lib.dsw_set_mix_mode(request.param) == 0
+    yield request.param
+    lib.dsw_set_mix_mode(prev)
+
+
+def _layer_from(g, dev):
+    from deepsphere_weather_b200 import layers as L
+
+    Fin, K, Fout = g["w"].shape
+    layer = L.ConvCheb(Fin, Fout, K, coo_from(g, "lap"), bias="b" in g.files).to(dev)
+    with torch.no_grad():
+        layer.weight.copy_(torch.from_numpy(g["w"]))
+        if "b" in g.files:
+            layer.bias.copy_(torch.from_numpy(g["b"]))
+    return layer
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_convcheb_matches_reference_golden(case, dev, mix_mode):
+    g = golden(case)
+    layer = _layer_from(g, dev)
+    x = torch.from_numpy(g["x"]).to(dev).requires_grad_(True)
+    from deepsphere_weather_b200 import _lib
+
+    launches0 = _lib.load().dsw_launch_count()
+    y = layer(x)
+    y.backward(torch.from_numpy(g["dy"]).to(dev))
+    assert _lib.load().dsw_launch_count() > launches0  # the CUDA library did the work
+    assert rel_err(y, g["y"]) < REL_TOL
+    assert rel_err(x.grad, g["dx"]) < REL_TOL
+    assert rel_err(layer.weight.grad, g["dw"]) < REL_TOL
+    if "b" in g.files:
+        assert rel_err(layer.bias.grad, g["db"]) < REL_TOL
+    assert rel_l2(y, g["y"]) < REL_TOL
+
+
+@pytest.mark.parametrize("B,nside,Fin,Fout,K", [(2, 4, 32, 48, 3), (3, 2, 3, 5, 5), (1, 4, 100, 36, 2), (5, 2, 64, 64, 4)])
+def test_convcheb_matches_oracle_seeded(B, nside, Fin, Fout, K, dev, mix_mode):
+    from deepsphere_weather_b200 import graphs as G
+    from deepsphere_weather_b200 import layers as L
+    from oracle import cheb_oracle as O
+
+    torch.manual_seed(B * 1000 + Fin)
+    lap = G.healpix_laplacian(nside)
+    V = lap.shape[0]
+    x = torch.randn(B, V, Fin)
+    w = torch.randn(Fin, K, Fout) * (2.0 / (Fin * K)) ** 0.5
+    b = torch.randn(Fout) * 0.1
+    dy = torch.randn(B, V, Fout)
+    xo, wo, bo = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yo = O.conv_cheb_layer(lap, xo, wo, bo)
+    yo.backward(dy)
+
+    layer = L.ConvCheb(Fin, Fout, K, lap).to(dev)
+    layer.set_parameters(w.to(dev), b.to(dev))
+    xg = x.to(dev).requires_grad_(True)
+    yg = layer(xg)
+    yg.backward(dy.to(dev))
+    assert rel_err(yg, yo) < REL_TOL
+    assert rel_err(xg.grad, xo.grad) < REL_TOL
+    assert rel_err(layer.weight.grad, wo.grad) < REL_TOL
+    assert rel_err(layer.bias.grad, bo.grad) < REL_TOL
+
+
+def test_convcheb_accepts_strided_views(dev):
+    """Pool outputs of the reference are [V',F,B]-ordered views (layers.py:963); any strides must work."""
+    from deepsphere_weather_b200 import graphs as G
+    from deepsphere_weather_b200 import layers as L
+    from oracle import cheb_oracle as O
+
+    torch.manual_seed(5)
+    lap = G.healpix_laplacian(2)
+    layer = L.ConvCheb(8, 6, 3, lap).to(dev)
+    w, b = layer.weight.detach().cpu(), layer.bias.detach().cpu()
+    base = torch.randn(48, 8, 3)                       # [V, F, B]
+    x_view = base.permute(2, 0, 1)                     # [B, V, F], feature stride != 1
+    padded = torch.randn(3, 48, 20)[:, :, 4:12]        # feature stride 1, padded node stride
+    for xv in (x_view, padded):
+        want = O.conv_cheb_layer(lap, xv, w, b)
+        xg = _to_device_keep_strides(xv, dev)
+        assert xg.stride() == xv.stride()
+        assert rel_err(layer(xg), want) < REL_TOL
+
+
+def _to_device_keep_strides(t, dev):
+    flat = _flat_storage(t).to(dev)
+    return torch.as_strided(flat, t.shape, t.stride(), t.storage_offset())
+
+
+def _flat_storage(t):
+    n = t.untyped_storage().nbytes() // t.element_size()
+    return torch.as_strided(t, (n,), (1,), 0)
+
+
+def test_cheb_terms_match_oracle_recurrence(dev):
+    from deepsphere_weather_b200 import functional as F_
+    from deepsphere_weather_b200 import graphs as G
+
+    torch.manual_seed(1)
+    lap = G.healpix_laplacian(4)
+    x = torch.randn(2, 192, 64)
+    got = F_.cheb_terms(x.to(dev), F_.plan_for(lap.to(dev)), 5).cpu()
+    flat = x.permute(1, 2, 0).reshape(192, -1)
+    t0, t1 = flat, torch.sparse.mm(lap, flat)
+    terms = [t1]
+    for _ in range(2, 5):
+        t0, t1 = t1, 2 * torch.sparse.mm(lap, t1) - t0
+        terms.append(t1)
+    for k, t in enumerate(terms):
+        want = t.reshape(192, 64, 2).permute(2, 0, 1)
+        assert rel_err(got[k], want) < 1e-5, k
+
+
+def test_errors_are_loud(dev):
+    from deepsphere_weather_b200 import graphs as G
+    from deepsphere_weather_b200 import layers as L
+
+    lap = G.healpix_laplacian(1)
+    layer = L.ConvCheb(4, 4, 2, lap)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        layer(torch.zeros(1, 12, 4))
+    layer = layer.to(dev)
+    with pytest.raises(ValueError, match="Input tensor shape does not match"):
+        layer(torch.zeros(1, 12, 5, device=dev))
+
+
+# ----------------------------------------------------------------------------------------------
+# pools
+# ----------------------------------------------------------------------------------------------
+
+
+def _pool_mats(g):
+    pool = sparse.coo_matrix((g["pool_dat"], (g["pool_row"], g["pool_col"])), shape=(48, 192))
+    unpool = sparse.coo_matrix((g["unpool_dat"], (g["unpool_row"], g["unpool_col"])), shape=(192, 48))
+    return pool, unpool
+
+
+@pytest.mark.parametrize("tag", ["interp", "maxarea"])
+def test_remap_pools_match_reference_golden(tag, dev):
+    from deepsphere_weather_b200 import layers as L
+
+    g = golden("pools")
+    pool_m, unpool_m = _pool_mats(g)
+    if tag == "interp":
+        pool, unpool = L.GeneralAvgPool(pool_m).to(dev), L.GeneralAvgUnpool(unpool_m).to(dev)
+    else:
+        pool, unpool = L.GeneralMaxAreaPool(pool_m).to(dev), L.GeneralMaxAreaUnpool(pool_m.T).to(dev)
+        assert torch.equal(pool.remap_matrix.cpu().indices(), coo_from(g, "maxarea_pool").indices())
+        assert torch.equal(unpool.remap_matrix.cpu().indices(), coo_from(g, "maxarea_unpool").indices())
+    x = torch.from_numpy(g["x"]).to(dev).requires_grad_(True)
+    yp, none = pool(x)
+    assert none is None
+    yu = unpool(yp)
+    yu.backward(torch.from_numpy(g[f"{tag}_g"]).to(dev))
+    assert rel_err(yp, g[f"{tag}_pooled"]) < 1e-6
+    assert rel_err(yu, g[f"{tag}_unpooled"]) < 1e-6
+    assert rel_err(x.grad, g[f"{tag}_dx"]) < 1e-6
+    if tag == "maxarea":  # pure gather: bit-exact
+        assert np.array_equal(yp.detach().cpu().numpy(), g["maxarea_pooled"])
+
+
+def test_maxval_pool_bit_exact(dev):
+    from deepsphere_weather_b200 import layers as L
+
+    g = golden("pools")
+    pool_m, unpool_m = _pool_mats(g)
+    pool, unpool = L.GeneralMaxValPool(pool_m).to(dev), L.GeneralMaxValUnpool(unpool_m).to(dev)
+    x = torch.from_numpy(g["x"]).to(dev).requires_grad_(True)
+    yp, idx = pool(x)
+    assert idx.dtype == torch.int64 and tuple(idx.shape) == g["maxval_index"].shape
+    assert np.array_equal(idx.cpu().numpy(), g["maxval_index"])
+    assert np.array_equal(yp.detach().cpu().numpy(), g["maxval_pooled"])
+    yu = unpool(yp, idx)
+    assert np.array_equal(yu.detach().cpu().numpy(), g["maxval_unpooled"])
+    yu.backward(torch.from_numpy(g["maxval_g"]).to(dev))
+    assert rel_err(x.grad, g["maxval_dx"]) < 1e-6
+
+
+@pytest.mark.parametrize("tag", ["hmax", "havg"])
+def test_healpix_pools_bit_exact(tag, dev):
+    from deepsphere_weather_b200 import layers as L
+
+    g = golden("pools")
+    pool, unpool = (L.HealpixMaxPool(4), L.HealpixMaxUnpool(4)) if tag == "hmax" else (L.HealpixAvgPool(4), L.HealpixAvgUnpool(4))
+    x = torch.from_numpy(g["x"]).to(dev).requires_grad_(True)
+    yp, idx = pool(x)
+    yu = unpool(yp, idx)
+    yu.backward(torch.from_numpy(g[f"{tag}_g"]).to(dev))
+    assert np.array_equal(yp.detach().cpu().numpy(), g[f"{tag}_pooled"])
+    assert np.array_equal(yu.detach().cpu().numpy(), g[f"{tag}_unpooled"])
+    if tag == "hmax":
+        assert idx.dtype == torch.int64 and np.array_equal(idx.cpu().numpy(), g["hmax_index"])
+    else:
+        assert idx is None
+    assert rel_err(x.grad, g[f"{tag}_dx"]) < 1e-6
+
+
+def test_pool_edge_cases(dev):
+    """NaN handling / ties follow torch.argmax and max_pool1d; batch of one; F not a multiple of 32."""
+    from deepsphere_weather_b200 import graphs as G
+    from deepsphere_weather_b200 import layers as L
+    from oracle import cheb_oracle as O
+
+    x = torch.randn(1, 48, 3)
+    x[0, 4:8, 0] = 2.0            # tie -> first
+    x[0, 9, 1] = float("nan")     # NaN wins
+    x[0, 12:16, 2] = float("-inf")
+    yo, io = O.healpix_max_pool(x, 4)
+    yg, ig = L.HealpixMaxPool(4)(x.to(dev))
+    assert torch.equal(io, ig.cpu())
+    assert np.array_equal(yo.numpy(), yg.cpu().numpy(), equal_nan=True)
+    pool_m, _ = G.random_overlap_pool_matrices(48, 12, seed=1)
+    mo = L.GeneralMaxValPool(pool_m)
+    yo, io = O.maxval_pool(mo.remap_matrix, x)
+    yg, ig = mo.to(dev)(x.to(dev))
+    assert torch.equal(io, ig.cpu())
+    assert np.array_equal(yo.numpy(), yg.cpu().numpy(), equal_nan=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# whole U-Net
+# ----------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("name,pool_method,K,seed", UNET_CASES)
+def test_unet_matches_reference_golden(name, pool_method, K, seed, dev, mix_mode):
+    from deepsphere_weather_b200 import models as M
+    from oracle.unet_oracle import fill_parameters
+
+    g = golden(name)
+    laps = [coo_from(g, f"lap{i}") for i in range(3)]
+    model = M.UNetSpherical(M.default_tensor_info(768), "healpix", {"subdivisions": 8, "nest": True},
+                            kernel_size_conv=K, pool_method=pool_method, laplacians=laps)
+    fill_parameters(model, seed)
+    model = model.to(dev)
+    y = model(torch.from_numpy(g["x"]).to(dev))
+    assert rel_err(y, g["y"]) < REL_TOL
+    loss = (y**2).mean()
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < REL_TOL * abs(float(g["loss"]))
+    grads = dict(model.named_parameters())
+    for n, ref_norm in zip([str(n) for n in g["grad_names"]], g["grad_norms"]):
+        got = grads[n].grad.norm().item()
+        assert abs(got - ref_norm) <= 2 * REL_TOL * max(ref_norm, 1e-6) + 1e-9, n
+    for key in g.files:
+        if key.startswith("grad__"):
+            assert rel_err(grads[key[6:]].grad, g[key]) < 2 * REL_TOL, key
+
+
+# ----------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: oracle on a slice + size-independent properties
+# ----------------------------------------------------------------------------------------------
+
+
+@pytest.fixture(scope="module")
+def cfg2(dev):
+    from deepsphere_weather_b200 import graphs as G
+    from deepsphere_weather_b200 import layers as L
+
+    torch.manual_seed(0)
+    lap = G.healpix_laplacian(32)
+    layer = L.ConvCheb(64, 64, 4, lap).to(dev)
+    with torch.no_grad():
+        layer.bias.normal_(0, 0.1)
+    x = torch.randn(32, 12288, 64, device=dev)
+    return lap, layer, x
+
+
+def test_cfg2_slices_match_oracle(cfg2, dev, mix_mode):
+    from oracle import cheb_oracle as O
+
+    lap, layer, x = cfg2
+    xg = x.clone().requires_grad_(True)
+    y = layer(xg)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    w, b = layer.weight.detach().cpu(), layer.bias.detach().cpu()
+    for s in (0, 31):
+        xs = x[s : s + 1].cpu().requires_grad_(True)
+        ys = O.conv_cheb_layer(lap, xs, w, b)
+        ys.backward(dy[s : s + 1].cpu())
+        assert rel_err(y[s : s + 1], ys) < REL_TOL
+        assert rel_err(xg.grad[s : s + 1], xs.grad) < REL_TOL
+
+
+def test_cfg2_properties(cfg2, dev, mix_mode):
+    from deepsphere_weather_b200 import functional as F_
+
+    lap, layer, x = cfg2
+    plan = F_.plan_for(layer.laplacian)
+    w = layer.weight.detach()
+    with torch.no_grad():
+        # linearity in x (no bias): f(a*x1 + x2) = a*f(x1) + f(x2)
+        x2 = torch.randn_like(x)
+        lhs = F_.cheb_conv(1.5 * x + x2, w, None, plan)
+        rhs = 1.5 * F_.cheb_conv(x, w, None, plan) + F_.cheb_conv(x2, w, None, plan)
+        assert rel_err(lhs, rhs) < REL_TOL
+        # samples are independent: permuting the batch permutes the output
+        perm = torch.randperm(x.shape[0], device=dev)
+        assert rel_err(F_.cheb_conv(x[perm], w, None, plan), F_.cheb_conv(x, w, None, plan)[perm]) < 1e-6
+        # weight gradient: dW of sum(y) equals the column sums of the Chebyshev terms
+        terms = F_.cheb_terms(x, plan, 4)
+        col = torch.stack([x.sum((0, 1))] + [terms[k].sum((0, 1)) for k in range(3)], 1)  # [Fin, K]
+    xg = x.clone().requires_grad_(False)
+    layer.zero_grad()
+    layer(xg).sum().backward()
+    want = col.unsqueeze(2).expand(-1, -1, 64)
+    assert rel_err(layer.weight.grad, want) < 5e-4  # sums of 393k fp32 terms
+    assert rel_err(layer.bias.grad, torch.full((64,), 32.0 * 12288)) < 1e-6
+
+
+def test_full_size_pool_round_trips(dev):
+    from deepsphere_weather_b200 import graphs as G
+    from deepsphere_weather_b200 import layers as L
+
+    torch.manual_seed(2)
+    V, F, B = 12288, 128, 32
+    x = torch.randn(B, V, F, device=dev)
+    pool_m, unpool_m = G.nested_pool_matrices(V, 4)
+    # exact nested matrices: interp pool == avg pool, maxval pool == max pool
+    ya, _ = L.HealpixAvgPool(4)(x)
+    yi, _ = L.GeneralAvgPool(pool_m).to(dev)(x)
+    assert rel_err(yi, ya) < 1e-6
+    ym, im = L.HealpixMaxPool(4)(x)
+    yv, iv = L.GeneralMaxValPool(pool_m).to(dev)(x)
+    assert torch.equal(ym, yv)
+    assert torch.equal(iv[0].view(F, B, V // 4).permute(1, 0, 2), im)
+    # unpool(pool(x)) restores exactly the selected entries and zero elsewhere
+    up = L.HealpixMaxUnpool(4)(ym, im)
+    up2 = L.GeneralMaxValUnpool(unpool_m).to(dev)(yv, iv)
+    assert torch.equal(up, up2)
+    assert torch.equal(up != 0, (up == x) & (up != 0))
+    assert int((up != 0).sum()) == B * (V // 4) * F
+    # pool(unpool(y)) == y  (pool @ unpool = I)
+    assert torch.equal(L.HealpixMaxPool(4)(up)[0], torch.maximum(ym, torch.zeros_like(ym)))
+    assert rel_err(L.HealpixAvgPool(4)(L.HealpixAvgUnpool(4)(ya))[0], ya) < 1e-6
