@@ -233,6 +233,14 @@ int wgrad_pick_nsplit(int64_t N, int32_t K, int32_t Fin, int32_t Fout) {
   return (int)std::max<int64_t>(1, std::min<int64_t>(ns, 1024));
 }
 
+int launch_wgrad_reduce(const float* partial, int32_t nsplit, int32_t K, int32_t Fin, int32_t Fout, float* dW,
+                        float* dbias, cudaStream_t st) {
+  const int64_t n_w = (int64_t)K * Fin * Fout;
+  const int64_t total = n_w + Fout;
+  wgrad_reduce_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(partial, nsplit, n_w, Fout, dW, dbias);
+  return check_launch();
+}
+
 int launch_wgrad_simt(const WgradArgs& a, cudaStream_t st) {
   const int ftiles = ceil_div(a.Fin, WT);
   int64_t rps = ceil_div64(a.N, a.nsplit);

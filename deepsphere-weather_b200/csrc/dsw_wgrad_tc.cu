@@ -1,0 +1,416 @@
+// tcgen05 weight gradient for sm_100a:
+//     dW[f][k][o] = sum_n T_k[n][f] * dY[n][o],      dbias[o] = sum_n dY[n][o]
+// (autograd of the channel mix, reference modules/layers.py:176-177, and of the bias add :375).
+//
+// The reduction runs over the rows n = (b, v), which is the *slow* index of both operands in memory
+// ([n][f] and [n][o], channel-last), so both UMMA operands are MN-major: a shared-memory row is one
+// n holding 64 consecutive channels (128 bytes of bf16), 8-row groups form the 1024-byte SWIZZLE_128B
+// atom, 64-channel blocks are LBO apart.  The global -> shared path therefore keeps the memory order:
+// coalesced float4 loads, split into bf16 hi/lo (3-term product, see dsw_mix_tc.cu), 8-byte stores.
+//
+// CTA = one 128 x BN tile of dW for one row range ("split"): TMEM lanes 0-63 / 64-127 hold two
+// (plane k, 64-channel block) half-tiles, BN <= 256 output channels in columns.  16 converter warps
+// stream units of 64 rows x 64 channels through a 4-deep register ring (64 KB of loads in flight per
+// SM — the small layers are HBM-bound); warp 16 issues the MMAs.  Partials go to the workspace and
+// are summed in a fixed order by wgrad_reduce_kernel (deterministic).
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "dsw_internal.cuh"
+
+namespace dsw {
+
+int launch_wgrad_reduce(const float* partial, int32_t nsplit, int32_t K, int32_t Fin, int32_t Fout, float* dW,
+                        float* dbias, cudaStream_t st);
+
+namespace wtc {
+
+constexpr int KB = 64;                 // rows (reduction) per stage
+constexpr int BLK = 64 * 128;          // bytes of one 64-row x 64-channel bf16 block image
+constexpr int CONV_THREADS = 512;
+constexpr int THREADS = CONV_THREADS + 32;
+constexpr int STAGES = 2;
+constexpr int RING = 4;                // units in flight per thread
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// MN-major SWIZZLE_128B descriptor: `lbo` = bytes between 64-element MN blocks, `sbo` = bytes between
+// 8-row K groups (cute::UMMA::make_umma_desc<Major::MN>: ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO))).
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t swz(uint32_t row, uint32_t chunk) {
+  return row * 128u + (((chunk ^ (row & 7u)) & 7u) << 4);
+}
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+struct WtcArgs {
+  WgradArgs w;
+  int32_t BN;          // output channels per CTA (multiple of 16, <= 256)
+  int32_t nb;          // ceil(BN / 64)
+  int32_t ftiles;      // ceil(Fin / 64)
+  int32_t tmem_cols;
+  int32_t kb_per_split;
+  int32_t desc_swap;   // debugging aid: exchange LBO / SBO
+};
+
+__global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WtcArgs P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ float bias_acc[256];
+  const WgradArgs& a = P.w;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int BN = P.BN, nb = P.nb;
+  const uint32_t a_img = 2u * BLK;            // one A image (hi or lo): two 64-channel blocks
+  const uint32_t b_img = (uint32_t)nb * BLK;  // one B image
+  const uint32_t stage_bytes = 2u * a_img + 2u * b_img;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bars = smem_base + STAGES * stage_bytes;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 16u + 8u * s; };
+  const uint32_t tmem_slot = bars + 32u;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * stage_bytes + 32);
+
+  if (t == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full(s), CONV_THREADS);
+      mbar_init(empty(s), 1);
+    }
+    fence_mbar_init();
+  }
+  if (t < 256) bias_acc[t] = 0.f;
+  if (warp == 16) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int mtile = blockIdx.x, ntile = blockIdx.y, split = blockIdx.z;
+  const int n_half = a.K * P.ftiles;
+  const int64_t r_begin = (int64_t)split * P.kb_per_split * KB;
+  const int64_t r_end = (r_begin + (int64_t)P.kb_per_split * KB < a.N) ? r_begin + (int64_t)P.kb_per_split * KB : a.N;
+  const int nkb = (r_end > r_begin) ? (int)((r_end - r_begin + KB - 1) / KB) : 0;
+  const int U = 2 + nb;  // units per row block: A half 0, A half 1, B blocks
+  const int o_base = ntile * BN;
+
+  if (warp < 16) {
+    // ================= converters =================
+    const int q = t & 15;        // float4 index inside a 64-channel row
+    const int r0 = t >> 4;       // rows r0 and r0 + 32 of the unit
+    // half-tile sources
+    const float* hsrc[2];
+    int64_t h_sB[2], h_sV[2];
+    int h_valid_f[2];
+    bool h_contig[2];
+    for (int h = 0; h < 2; ++h) {
+      h_contig[h] = true;
+      const int ht = mtile * 2 + h;
+      if (ht < n_half) {
+        const int k = ht / P.ftiles, f0 = (ht - k * P.ftiles) * 64;
+        hsrc[h] = a.T[k] + f0;
+        h_sB[h] = a.t_sB[k], h_sV[h] = a.t_sV[k];
+        h_valid_f[h] = a.Fin - f0;  // channels available from f0
+        h_contig[h] = (h_sB[h] == (int64_t)a.rows_per_batch * h_sV[h]);
+      } else {
+        hsrc[h] = nullptr, h_sB[h] = 0, h_sV[h] = 0, h_valid_f[h] = 0;
+      }
+    }
+    const bool do_bias = (mtile == 0) && (a.dbias != nullptr);
+    float4 bsum[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bsum[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    const int total_units = nkb * U;
+    float4 ring[RING][2];
+
+    auto load_unit = [&](int j, float4 (&dst)[2]) {
+      const int kb = j / U, u = j - kb * U;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int64_t n = r_begin + (int64_t)kb * KB + r0 + 32 * i;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n < r_end) {
+          if (u < 2) {
+            const int avail = h_valid_f[u] - q * 4;
+            if (avail > 0) {
+              const float* src;
+              if (h_contig[u]) {
+                src = hsrc[u] + n * h_sV[u] + q * 4;
+              } else {
+                const uint32_t bb = (uint32_t)n / (uint32_t)a.rows_per_batch;
+                src = hsrc[u] + (int64_t)bb * h_sB[u] + (int64_t)((uint32_t)n - bb * (uint32_t)a.rows_per_batch) * h_sV[u] + q * 4;
+              }
+              if (avail >= 4 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+                v = __ldg(reinterpret_cast<const float4*>(src));
+              } else {
+                v.x = __ldg(src);
+                if (avail > 1) v.y = __ldg(src + 1);
+                if (avail > 2) v.z = __ldg(src + 2);
+                if (avail > 3) v.w = __ldg(src + 3);
+              }
+            }
+          } else {
+            const int o = o_base + (u - 2) * 64 + q * 4;
+            const int avail = a.Fout - o;
+            if (avail > 0) {
+              const float* src = a.dY + n * a.Fout + o;
+              if (avail >= 4 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+                v = __ldg(reinterpret_cast<const float4*>(src));
+              } else {
+                v.x = __ldg(src);
+                if (avail > 1) v.y = __ldg(src + 1);
+                if (avail > 2) v.z = __ldg(src + 2);
+                if (avail > 3) v.w = __ldg(src + 3);
+              }
+            }
+          }
+        }
+        dst[i] = v;
+      }
+    };
+
+    auto store_unit = [&](int j, const float4 (&src)[2]) {
+      const int kb = j / U, u = j - kb * U;
+      const int s = kb & 1;
+      if (u == 0 && kb >= STAGES) {
+        mbar_wait(empty(s), ((kb >> 1) - 1) & 1);
+        tc_fence_after();
+      }
+      uint8_t* st = smem_gen + s * stage_bytes;
+      uint8_t* hi_img = (u < 2) ? st + u * BLK : st + 2u * a_img + (u - 2) * BLK;
+      uint8_t* lo_img = (u < 2) ? hi_img + a_img : hi_img + b_img;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint32_t row = r0 + 32 * i;
+        __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+        split_bf16(src[i].x, h0, l0);
+        split_bf16(src[i].y, h1, l1);
+        split_bf16(src[i].z, h2, l2);
+        split_bf16(src[i].w, h3, l3);
+        const uint32_t off = swz(row, q >> 1) + (q & 1) * 8;
+        *reinterpret_cast<uint2*>(hi_img + off) = make_uint2(pack2(h0, h1), pack2(h2, h3));
+        *reinterpret_cast<uint2*>(lo_img + off) = make_uint2(pack2(l0, l1), pack2(l2, l3));
+      }
+      if (do_bias && u >= 2) {
+        float4& b = bsum[u - 2];
+        b.x += src[0].x + src[1].x, b.y += src[0].y + src[1].y;
+        b.z += src[0].z + src[1].z, b.w += src[0].w + src[1].w;
+      }
+      if (u == U - 1) {
+        fence_proxy_async();
+        mbar_arrive(full(s));
+      }
+    };
+
+#pragma unroll
+    for (int d = 0; d < RING; ++d)
+      if (d < total_units) load_unit(d, ring[d]);
+    for (int j0 = 0; j0 < total_units; j0 += RING) {
+#pragma unroll
+      for (int d = 0; d < RING; ++d) {
+        const int j = j0 + d;
+        if (j < total_units) {
+          store_unit(j, ring[d]);
+          if (j + RING < total_units) load_unit(j + RING, ring[d]);
+        }
+      }
+    }
+
+    // ---- dbias partial (fp32, CTA-local reduction through shared memory) ----
+    if (do_bias) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < nb) {
+          atomicAdd(&bias_acc[j * 64 + q * 4 + 0], bsum[j].x);
+          atomicAdd(&bias_acc[j * 64 + q * 4 + 1], bsum[j].y);
+          atomicAdd(&bias_acc[j * 64 + q * 4 + 2], bsum[j].z);
+          atomicAdd(&bias_acc[j * 64 + q * 4 + 3], bsum[j].w);
+        }
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(CONV_THREADS));
+
+    // ================= epilogue: TMEM -> partial[split] =================
+    const int64_t prow = (int64_t)a.K * a.Fin + 1;
+    float* __restrict__ Pp = a.partial + (int64_t)split * prow * a.Fout;
+    if (do_bias && t < BN && o_base + t < a.Fout) Pp[(prow - 1) * a.Fout + o_base + t] = bias_acc[t];
+
+    if (nkb > 0) {
+      const int last = nkb - 1;
+      mbar_wait(empty(last & 1), (last >> 1) & 1);
+      tc_fence_after();
+    }
+    const int quarter = warp & 3, part = warp >> 2;  // 4 lane quarters x 4 column parts
+    const int L = quarter * 32 + lane;
+    const int h = L >> 6, fl = L & 63;
+    const int ht = mtile * 2 + h;
+    int64_t m = -1;
+    if (ht < n_half) {
+      const int k = ht / P.ftiles, f0 = (ht - k * P.ftiles) * 64;
+      if (f0 + fl < a.Fin) m = (int64_t)(f0 + fl) * a.K + k;
+    }
+    const int chunks = BN / 16;
+    for (int ch = (chunks * part) / 4; ch < (chunks * (part + 1)) / 4; ++ch) {
+      uint32_t r[16];
+      if (nkb > 0) {
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 16), r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) r[e] = 0u;
+      }
+      if (m < 0) continue;
+      const int o0 = o_base + ch * 16;
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (o0 + e < a.Fout) Pp[m * a.Fout + o0 + e] = __uint_as_float(r[e]);
+    }
+  } else if (lane == 0) {
+    // ================= MMA issuer =================
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t lbo = P.desc_swap ? 1024u : (uint32_t)BLK;
+    const uint32_t sbo = P.desc_swap ? (uint32_t)BLK : 1024u;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb & 1;
+      mbar_wait(full(s), (kb >> 1) & 1);
+      tc_fence_after();
+      const uint32_t st = smem_base + s * stage_bytes;
+      const uint32_t Ah = st, Al = st + a_img, Bh = st + 2u * a_img, Bl = Bh + b_img;
+      for (int ks = 0; ks < KB / 16; ++ks) {
+        const uint32_t adv = (uint32_t)ks * 2048u;  // 16 rows = two 8-row groups
+        const uint64_t dAh = make_desc_mn(Ah + adv, lbo, sbo), dAl = make_desc_mn(Al + adv, lbo, sbo);
+        const uint64_t dBh = make_desc_mn(Bh + adv, lbo, sbo), dBl = make_desc_mn(Bl + adv, lbo, sbo);
+        umma_bf16(tmem_base, dAh, dBh, idesc, (kb | ks) != 0);
+        umma_bf16(tmem_base, dAh, dBl, idesc, 1u);
+        umma_bf16(tmem_base, dAl, dBh, idesc, 1u);
+      }
+      umma_commit(empty(s));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+}
+
+static size_t smem_bytes_for(int nb) { return (size_t)STAGES * (2 * 2 * BLK + 2 * nb * BLK) + 1024 + 64; }
+
+}  // namespace wtc
+
+static void wgrad_tc_geometry(int64_t N, int32_t K, int32_t Fin, int32_t Fout, int& BN, int& ntiles, int& mtiles,
+                              int& nsplit, int& kb_per_split) {
+  BN = std::min(256, (Fout + 15) / 16 * 16);
+  ntiles = (Fout + BN - 1) / BN;
+  const int ftiles = (Fin + 63) / 64;
+  mtiles = (K * ftiles + 1) / 2;
+  const int64_t total_kb = (N + wtc::KB - 1) / wtc::KB;
+  int64_t ns = std::max<int64_t>(1, 148 / ((int64_t)mtiles * ntiles));
+  ns = std::min<int64_t>(ns, std::max<int64_t>(1, total_kb / 4));
+  kb_per_split = (int)((total_kb + ns - 1) / ns);
+  nsplit = (int)((total_kb + kb_per_split - 1) / kb_per_split);
+}
+
+size_t wgrad_tc_partial_bytes(int64_t N, int32_t K, int32_t Fin, int32_t Fout) {
+  int BN, ntiles, mtiles, nsplit, kbps;
+  wgrad_tc_geometry(N, K, Fin, Fout, BN, ntiles, mtiles, nsplit, kbps);
+  return (size_t)nsplit * ((size_t)K * Fin + 1) * Fout * sizeof(float);
+}
+
+int launch_wgrad_tc(const WgradArgs& a, size_t partial_bytes, cudaStream_t st) {
+  if (!a.partial) return DSW_ERR_UNSUPPORTED;
+  if (partial_bytes < wgrad_tc_partial_bytes(a.N, a.K, a.Fin, a.Fout)) return DSW_ERR_UNSUPPORTED;
+  if (a.N >= (int64_t)1 << 31) return DSW_ERR_UNSUPPORTED;
+  wtc::WtcArgs P;
+  P.w = a;
+  int ntiles, mtiles, nsplit;
+  wgrad_tc_geometry(a.N, a.K, a.Fin, a.Fout, P.BN, ntiles, mtiles, nsplit, P.kb_per_split);
+  P.w.nsplit = nsplit;
+  P.nb = (P.BN + 63) / 64;
+  P.ftiles = (a.Fin + 63) / 64;
+  int cols = 32;
+  while (cols < P.BN) cols <<= 1;
+  P.tmem_cols = cols;
+  static const int swap_env = [] {
+    const char* e = std::getenv("DSW_WGRAD_DESC_SWAP");
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
+  P.desc_swap = swap_env;
+
+  const size_t smem = wtc::smem_bytes_for(P.nb);
+  static std::atomic<bool> attr_set{false};
+  if (!attr_set.exchange(true))
+    DSW_CUDA_TRY(cudaFuncSetAttribute(wtc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  dim3 grid(mtiles, ntiles, nsplit);
+  wtc::wgrad_tc_kernel<<<grid, wtc::THREADS, smem, st>>>(P);
+  DSW_TRY(check_launch());
+  return launch_wgrad_reduce(a.partial, nsplit, a.K, a.Fin, a.Fout, a.dW, a.dbias, st);
+}
+
+}  // namespace dsw
