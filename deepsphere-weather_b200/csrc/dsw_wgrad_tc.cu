@@ -16,7 +16,6 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
-#include <cstdlib>
 
 #include "dsw_internal.cuh"
 
@@ -117,7 +116,6 @@ struct WtcArgs {
   int32_t ftiles;      // ceil(Fin / 64)
   int32_t tmem_cols;
   int32_t kb_per_split;
-  int32_t desc_swap;   // debugging aid: exchange LBO / SBO
 };
 
 __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WtcArgs P) {
@@ -336,8 +334,8 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
     // ================= MMA issuer =================
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t lbo = P.desc_swap ? 1024u : (uint32_t)BLK;
-    const uint32_t sbo = P.desc_swap ? (uint32_t)BLK : 1024u;
+    const uint32_t lbo = (uint32_t)BLK;  // between 64-channel blocks
+    const uint32_t sbo = 1024u;          // between 8-row groups
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb & 1;
       mbar_wait(full(s), (kb >> 1) & 1);
@@ -397,16 +395,12 @@ int launch_wgrad_tc(const WgradArgs& a, size_t partial_bytes, cudaStream_t st) {
   int cols = 32;
   while (cols < P.BN) cols <<= 1;
   P.tmem_cols = cols;
-  static const int swap_env = [] {
-    const char* e = std::getenv("DSW_WGRAD_DESC_SWAP");
-    return (e && e[0] == '1') ? 1 : 0;
-  }();
-  P.desc_swap = swap_env;
 
   const size_t smem = wtc::smem_bytes_for(P.nb);
   static std::atomic<bool> attr_set{false};
   if (!attr_set.exchange(true))
-    DSW_CUDA_TRY(cudaFuncSetAttribute(wtc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DSW_CUDA_TRY(cudaFuncSetAttribute(wtc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)wtc::smem_bytes_for(4)));  // + 1 KB static bias_acc <= 227 KB
   dim3 grid(mtiles, ntiles, nsplit);
   wtc::wgrad_tc_kernel<<<grid, wtc::THREADS, smem, st>>>(P);
   DSW_TRY(check_launch());
