@@ -8,6 +8,8 @@
 
 #include "dsw.h"
 
+#define DSW_TILE_BLOCKS 32
+
 struct dsw_csr {
   int32_t n_rows = 0, n_cols = 0;
   int64_t nnz = 0;
@@ -26,6 +28,22 @@ struct dsw_rb {
   int32_t n_blocks = 0;
   int32_t max_union = 0;
   int64_t total_union = 0;
+  int32_t tile_entries_max = 0;  // max union entries over runs of 32 consecutive row-blocks
+  // Tiles of DSW_TILE_BLOCKS consecutive row-blocks: the sorted list of distinct source rows a tile
+  // gathers (staged in shared memory by bulk async copies) and, per union entry, its position in
+  // that list.
+  int32_t n_tiles = 0;
+  int32_t tile_rows_max = 0;
+  int32_t* tile_ptr = nullptr;   // [n_tiles + 1] offsets into tile_row
+  int32_t* tile_row = nullptr;   // source row ids, ascending inside a tile
+  uint16_t* lidx = nullptr;      // [total_union] local index of ucol[e] inside its tile's list
+  // Entry-major padded panels of a tile: entry u of row-block slot s at [tp_ptr[t] + u][s]; every
+  // row-block of the tile is padded to the tile's longest union with zero weights / offset 0, so the
+  // 32 slots of one entry step are contiguous (conflict-free broadcast reads, uniform trip counts).
+  int32_t tile_len_max = 0;      // max entry steps of a tile
+  int32_t* tp_ptr = nullptr;     // [n_tiles + 1] cumulative entry steps
+  float4* tp_val = nullptr;      // [total_steps][32] R = 4 weights
+  uint32_t* tp_off = nullptr;    // [total_steps][32] byte offset of the source row inside the staged tile (256 B rows)
   int32_t* blkptr = nullptr;   // [n_blocks + 1] offsets into ucol / uval panels
   int32_t* ucol = nullptr;     // [total_union]
   float* uval = nullptr;       // [total_union * R]  (entry u, row r) at uval[u*R + r]
@@ -42,6 +60,7 @@ namespace dsw {
 
 extern std::atomic<int64_t> g_launches;
 extern std::atomic<int> g_mix_mode;
+extern std::atomic<int64_t> g_options[DSW_OPT_COUNT];
 
 void set_cuda_error(cudaError_t e);
 

@@ -241,17 +241,13 @@ int launch_wgrad_reduce(const float* partial, int32_t nsplit, int32_t K, int32_t
   return check_launch();
 }
 
+// Writes a.nsplit partials at a.partial; the caller sums them with launch_wgrad_reduce.
 int launch_wgrad_simt(const WgradArgs& a, cudaStream_t st) {
   const int ftiles = ceil_div(a.Fin, WT);
   int64_t rps = ceil_div64(a.N, a.nsplit);
   rps = ceil_div64(rps, WR) * WR;
   dim3 grid(a.K * ftiles + 1, ceil_div(a.Fout, WT), a.nsplit);
   wgrad_simt_kernel<<<grid, 256, 0, st>>>(a, ftiles, rps);
-  DSW_TRY(check_launch());
-  const int64_t n_w = (int64_t)a.K * a.Fin * a.Fout;
-  const int64_t total = n_w + a.Fout;
-  wgrad_reduce_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(a.partial, a.nsplit, n_w, a.Fout, a.dW,
-                                                                        a.dbias);
   return check_launch();
 }
 

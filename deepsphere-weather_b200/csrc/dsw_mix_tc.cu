@@ -362,7 +362,9 @@ size_t mix_tc_workspace_bytes(int32_t P, int32_t Ka, int32_t Nc) {
 }
 
 // `prep` = workspace of mix_tc_workspace_bytes(); nullptr -> unsupported (caller falls back).
-int launch_mix_tc_ws(const MixArgs& a, void* prep, size_t prep_bytes, cudaStream_t st) {
+// do_prep = false reuses the weight images written by an earlier call with the same B operand
+// (the per-chunk calls of one convolution share them).
+int launch_mix_tc_ws(const MixArgs& a, void* prep, size_t prep_bytes, bool do_prep, cudaStream_t st) {
   if (!prep || a.Nc < 1 || a.Ka < 1 || a.N < 1) return DSW_ERR_UNSUPPORTED;
   if (prep_bytes < mix_tc_workspace_bytes(a.P, a.Ka, a.Nc)) return DSW_ERR_UNSUPPORTED;
   if (reinterpret_cast<uintptr_t>(prep) & 15) return DSW_ERR_UNSUPPORTED;
@@ -376,9 +378,11 @@ int launch_mix_tc_ws(const MixArgs& a, void* prep, size_t prep_bytes, cudaStream
   P.bprep = static_cast<const uint8_t*>(prep);
   const int n_tiles = (a.Nc + P.BN - 1) / P.BN;
 
-  const int64_t chunks = (int64_t)n_tiles * a.P * P.nkb * P.BN * 8;
-  tc::mix_tc_prep_kernel<<<(unsigned)ceil_div64(chunks, 256), 256, 0, st>>>(P, static_cast<uint8_t*>(prep), n_tiles);
-  DSW_TRY(check_launch());
+  if (do_prep) {
+    const int64_t chunks = (int64_t)n_tiles * a.P * P.nkb * P.BN * 8;
+    tc::mix_tc_prep_kernel<<<(unsigned)ceil_div64(chunks, 256), 256, 0, st>>>(P, static_cast<uint8_t*>(prep), n_tiles);
+    DSW_TRY(check_launch());
+  }
 
   bool vec4 = (a.Ka % 4 == 0);
   for (int p = 0; p < a.P && vec4; ++p)

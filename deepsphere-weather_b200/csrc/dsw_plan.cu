@@ -14,6 +14,7 @@ namespace dsw {
 
 std::atomic<int64_t> g_launches{0};
 std::atomic<int> g_mix_mode{1};
+std::atomic<int64_t> g_options[DSW_OPT_COUNT] = {};
 
 static thread_local cudaError_t t_last_err = cudaSuccess;
 void set_cuda_error(cudaError_t e) { t_last_err = e; }
@@ -72,7 +73,58 @@ struct HostRb {
   int32_t R = 0, n_blocks = 0, max_union = 0;
   std::vector<int32_t> blkptr, ucol;
   std::vector<float> uval;
+  // tiles of DSW_TILE_BLOCKS row-blocks
+  int32_t n_tiles = 0, tile_rows_max = 0;
+  std::vector<int32_t> tile_ptr, tile_row;
+  std::vector<uint16_t> lidx;
+  int32_t tile_len_max = 0;
+  std::vector<int32_t> tp_ptr;
+  std::vector<float> tp_val;      // 4 floats per (step, slot)
+  std::vector<uint32_t> tp_off;
 };
+
+static void build_tiles(HostRb& rb) {
+  rb.n_tiles = (rb.n_blocks + DSW_TILE_BLOCKS - 1) / DSW_TILE_BLOCKS;
+  rb.tile_ptr.assign(static_cast<size_t>(rb.n_tiles) + 1, 0);
+  rb.lidx.assign(rb.ucol.size(), 0);
+  std::vector<int32_t> rows;
+  bool fits16 = true;
+  for (int32_t t = 0; t < rb.n_tiles; ++t) {
+    const int32_t e0 = rb.blkptr[t * DSW_TILE_BLOCKS];
+    const int32_t e1 = rb.blkptr[std::min(rb.n_blocks, (t + 1) * DSW_TILE_BLOCKS)];
+    rows.assign(rb.ucol.begin() + e0, rb.ucol.begin() + e1);
+    std::sort(rows.begin(), rows.end());
+    rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+    if (rows.size() > 65535) fits16 = false;
+    for (int32_t e = e0; e < e1 && fits16; ++e)
+      rb.lidx[e] = static_cast<uint16_t>(std::lower_bound(rows.begin(), rows.end(), rb.ucol[e]) - rows.begin());
+    rb.tile_row.insert(rb.tile_row.end(), rows.begin(), rows.end());
+    rb.tile_ptr[t + 1] = static_cast<int32_t>(rb.tile_row.size());
+    rb.tile_rows_max = std::max<int32_t>(rb.tile_rows_max, static_cast<int32_t>(rows.size()));
+  }
+  if (!fits16) {  // tile layout unusable; kernels fall back
+    rb.n_tiles = 0, rb.tile_rows_max = 0;
+    return;
+  }
+  // entry-major padded panels
+  rb.tp_ptr.assign(static_cast<size_t>(rb.n_tiles) + 1, 0);
+  for (int32_t t = 0; t < rb.n_tiles; ++t) {
+    const int32_t b0 = t * DSW_TILE_BLOCKS, b1 = std::min(rb.n_blocks, b0 + DSW_TILE_BLOCKS);
+    int32_t len = 0;
+    for (int32_t b = b0; b < b1; ++b) len = std::max(len, rb.blkptr[b + 1] - rb.blkptr[b]);
+    rb.tile_len_max = std::max(rb.tile_len_max, len);
+    const size_t base = static_cast<size_t>(rb.tp_ptr[t]) * DSW_TILE_BLOCKS;
+    rb.tp_val.resize((base + static_cast<size_t>(len) * DSW_TILE_BLOCKS) * 4, 0.f);
+    rb.tp_off.resize(base + static_cast<size_t>(len) * DSW_TILE_BLOCKS, 0u);
+    for (int32_t b = b0; b < b1; ++b)
+      for (int32_t e = rb.blkptr[b], u = 0; e < rb.blkptr[b + 1]; ++e, ++u) {
+        const size_t at = base + static_cast<size_t>(u) * DSW_TILE_BLOCKS + (b - b0);
+        for (int r = 0; r < 4; ++r) rb.tp_val[at * 4 + r] = rb.uval[static_cast<size_t>(e) * 4 + r];
+        rb.tp_off[at] = static_cast<uint32_t>(rb.lidx[e]) * 256u;
+      }
+    rb.tp_ptr[t + 1] = rb.tp_ptr[t] + len;
+  }
+}
 
 static HostRb build_rb(const HostCsr& a, int32_t R) {
   HostRb rb;
@@ -96,6 +148,7 @@ static HostRb build_rb(const HostCsr& a, int32_t R) {
     rb.blkptr[blk + 1] = static_cast<int32_t>(rb.ucol.size());
     rb.max_union = std::max<int32_t>(rb.max_union, static_cast<int32_t>(uni.size()));
   }
+  if (R == 4) build_tiles(rb);
   return rb;
 }
 
@@ -151,10 +204,27 @@ static cudaError_t upload_rb(dsw_rb* d, const HostRb& h, cudaStream_t st) {
   d->n_blocks = h.n_blocks;
   d->max_union = h.max_union;
   d->total_union = static_cast<int64_t>(h.ucol.size());
+  d->tile_entries_max = 0;
+  for (int32_t b0 = 0; b0 < h.n_blocks; b0 += 32)
+    d->tile_entries_max = std::max(d->tile_entries_max, h.blkptr[std::min(h.n_blocks, b0 + 32)] - h.blkptr[b0]);
   cudaError_t e;
   if ((e = upload(&d->blkptr, h.blkptr, st)) != cudaSuccess) return e;
   if ((e = upload(&d->ucol, h.ucol, st)) != cudaSuccess) return e;
-  return upload(&d->uval, h.uval, st);
+  if ((e = upload(&d->uval, h.uval, st)) != cudaSuccess) return e;
+  d->n_tiles = h.n_tiles;
+  d->tile_rows_max = h.tile_rows_max;
+  if (h.n_tiles > 0) {
+    if ((e = upload(&d->tile_ptr, h.tile_ptr, st)) != cudaSuccess) return e;
+    if ((e = upload(&d->tile_row, h.tile_row, st)) != cudaSuccess) return e;
+    if ((e = upload(&d->lidx, h.lidx, st)) != cudaSuccess) return e;
+    d->tile_len_max = h.tile_len_max;
+    if ((e = upload(&d->tp_ptr, h.tp_ptr, st)) != cudaSuccess) return e;
+    float* tv = nullptr;
+    if ((e = upload(&tv, h.tp_val, st)) != cudaSuccess) return e;
+    d->tp_val = reinterpret_cast<float4*>(tv);
+    if ((e = upload(&d->tp_off, h.tp_off, st)) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 static void free_csr(dsw_csr* c) {
@@ -167,6 +237,12 @@ static void free_rb(dsw_rb* r) {
   cudaFree(r->blkptr);
   cudaFree(r->ucol);
   cudaFree(r->uval);
+  cudaFree(r->tile_ptr);
+  cudaFree(r->tile_row);
+  cudaFree(r->lidx);
+  cudaFree(r->tp_ptr);
+  cudaFree(r->tp_val);
+  cudaFree(r->tp_off);
   *r = dsw_rb{};
 }
 
@@ -211,6 +287,15 @@ int dsw_set_mix_mode(int mode) {
   return DSW_OK;
 }
 int dsw_get_mix_mode(void) { return g_mix_mode.load(); }
+int dsw_set_option(int key, int64_t value) {
+  if (key < 0 || key >= DSW_OPT_COUNT || value < 0) return DSW_ERR_BAD_ARGUMENT;
+  g_options[key].store(value);
+  return DSW_OK;
+}
+int64_t dsw_get_option(int key) {
+  if (key < 0 || key >= DSW_OPT_COUNT) return -1;
+  return g_options[key].load();
+}
 
 int dsw_plan_create(int32_t n_rows, int32_t n_cols, int64_t nnz, const int64_t* coo_row,
                     const int64_t* coo_col, const float* coo_val, void* stream, dsw_plan** out) {

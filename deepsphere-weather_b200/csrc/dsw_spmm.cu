@@ -15,6 +15,8 @@
 namespace dsw {
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// L2-only (cache-global) load: streaming operands that are read once per kernel
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
 template <int R>
 __global__ void __launch_bounds__(512) hop_rb_kernel(const int32_t* __restrict__ blkptr,
@@ -161,6 +163,347 @@ __global__ void __launch_bounds__(256) hop_csr_kernel(const int32_t* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// hop_tile_kernel — the production hop for row-block (R = 4) operators.
+//
+// CTA = TB consecutive row-blocks (128 rows) x one 64-channel slab x `ns` samples.  The tile's slice
+// of the union panels (column list -> pre-multiplied byte offsets, R x U weights) is staged in shared
+// memory once and reused for every sample, so the inner loop issues two broadcast LDS (offset,
+// weights) per union entry and NF4 gathers of 16 bytes that each feed R packed FMAs (FFMA2).
+// 8 lanes own one row-block: lane l reads float4 columns l and l + 8 of the slab, i.e. the 8 lanes
+// of a row-block touch one full 128-byte line per gather instruction.
+// ---------------------------------------------------------------------------------------------
+constexpr int TILE_BLOCKS = 32;   // row-blocks per CTA
+constexpr int TILE_THREADS = 256; // 8 lanes per row-block
+
+__device__ __forceinline__ void fma4(float4& acc, float w, const float4& x) {
+  const float2 ww = make_float2(w, w);
+  float2 lo = __ffma2_rn(ww, make_float2(x.x, x.y), make_float2(acc.x, acc.y));
+  float2 hi = __ffma2_rn(ww, make_float2(x.z, x.w), make_float2(acc.z, acc.w));
+  acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+template <int NF4>
+__global__ void __launch_bounds__(TILE_THREADS, 3) hop_tile_kernel(const int32_t* __restrict__ blkptr,
+                                                                    const int32_t* __restrict__ ucol,
+                                                                    const float4* __restrict__ uval, int32_t n_blocks,
+                                                                    int32_t n_rows, int32_t ns, HopArgs a) {
+  extern __shared__ __align__(16) uint8_t tile_smem[];
+  const int tid = threadIdx.x;
+  const int blk0 = blockIdx.x * TILE_BLOCKS;
+  const int blk1 = min(blk0 + TILE_BLOCKS, n_blocks);
+  const int e0 = __ldg(blkptr + blk0);
+  const int ne = __ldg(blkptr + blk1) - e0;
+  float4* s_val = reinterpret_cast<float4*>(tile_smem);
+  uint32_t* s_off = reinterpret_cast<uint32_t*>(tile_smem + (size_t)((ne + 3) & ~3) * 16);
+  const uint32_t row_bytes = (uint32_t)a.x_sV * 4u;
+  for (int i = tid; i < ne; i += TILE_THREADS) {
+    s_val[i] = __ldg(uval + e0 + i);
+    s_off[i] = (uint32_t)__ldg(ucol + e0 + i) * row_bytes;
+  }
+  __syncthreads();
+
+  const int slot = tid >> 3, l8 = tid & 7;
+  const int blk = blk0 + slot;
+  if (blk >= n_blocks) return;
+  const int u0 = __ldg(blkptr + blk) - e0, u1 = __ldg(blkptr + blk + 1) - e0;
+  const int c4 = blockIdx.y * (8 * NF4) + l8;  // first float4 column of this lane
+  const int nf4 = a.F >> 2;
+  bool ok[NF4];
+#pragma unroll
+  for (int j = 0; j < NF4; ++j) ok[j] = (c4 + 8 * j) < nf4;
+  if (!ok[0]) return;
+
+  const int b_begin = blockIdx.z * ns, b_end = min(b_begin + ns, a.B);
+  for (int b = b_begin; b < b_end; ++b) {
+    const char* __restrict__ xb = reinterpret_cast<const char*>(a.X + (int64_t)b * a.x_sB + c4 * 4);
+    float4 acc[4][NF4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int j = 0; j < NF4; ++j) acc[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    int u = u0;
+#pragma unroll 1
+    for (; u + 2 <= u1; u += 2) {
+      const uint32_t oa = s_off[u], ob = s_off[u + 1];
+      const float4 wa = s_val[u], wb = s_val[u + 1];
+      float4 xa[NF4], xv[NF4];
+#pragma unroll
+      for (int j = 0; j < NF4; ++j) {
+        xa[j] = ok[j] ? ldg4(reinterpret_cast<const float*>(xb + oa + 128 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xv[j] = ok[j] ? ldg4(reinterpret_cast<const float*>(xb + ob + 128 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < NF4; ++j) {
+        fma4(acc[0][j], wa.x, xa[j]), fma4(acc[1][j], wa.y, xa[j]);
+        fma4(acc[2][j], wa.z, xa[j]), fma4(acc[3][j], wa.w, xa[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < NF4; ++j) {
+        fma4(acc[0][j], wb.x, xv[j]), fma4(acc[1][j], wb.y, xv[j]);
+        fma4(acc[2][j], wb.z, xv[j]), fma4(acc[3][j], wb.w, xv[j]);
+      }
+    }
+    if (u < u1) {
+      const uint32_t oa = s_off[u];
+      const float4 wa = s_val[u];
+#pragma unroll
+      for (int j = 0; j < NF4; ++j) {
+        if (!ok[j]) continue;
+        const float4 xa = ldg4(reinterpret_cast<const float*>(xb + oa + 128 * j));
+        fma4(acc[0][j], wa.x, xa), fma4(acc[1][j], wa.y, xa);
+        fma4(acc[2][j], wa.z, xa), fma4(acc[3][j], wa.w, xa);
+      }
+    }
+
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int row = blk * 4 + r;
+      if (row >= n_rows) break;
+#pragma unroll
+      for (int j = 0; j < NF4; ++j) {
+        if (!ok[j]) continue;
+        const int64_t col = (int64_t)(c4 + 8 * j) * 4;
+        float4 o = make_float4(a.alpha * acc[r][j].x, a.alpha * acc[r][j].y, a.alpha * acc[r][j].z,
+                               a.alpha * acc[r][j].w);
+        if (a.Z) {
+          const float4 z = ldg4(a.Z + b * a.z_sB + row * a.z_sV + col);
+          o.x = fmaf(a.beta, z.x, o.x), o.y = fmaf(a.beta, z.y, o.y);
+          o.z = fmaf(a.beta, z.z, o.z), o.w = fmaf(a.beta, z.w, o.w);
+        }
+        if (a.G) {
+          const float4 g = ldg4(a.G + b * a.g_sB + row * a.g_sV + col);
+          o.x += g.x, o.y += g.y, o.z += g.z, o.w += g.w;
+        }
+        *reinterpret_cast<float4*>(a.O + b * a.o_sB + row * a.o_sV + col) = o;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// hop_team_kernel — the production hop for row-block (R = 4) operators.
+//
+// CTA = one tile of DSW_TILE_BLOCKS consecutive row-blocks (128 rows).  The tile's entry-major
+// padded union panels (R weights + the local source-row offset per entry step and row-block) and its
+// source-row list are staged in shared memory once per CTA.  Up to three independent 128-thread
+// *teams* then walk the CTA's work items (sample, 64-channel slab): a team stages the distinct source
+// rows the tile gathers for its item (own rows + halo; 16-byte cp.async.cg straight from L2, ~64 KB
+// in flight per team, no registers), computes the neighbour sums entirely out of shared memory and
+// writes the 128 output rows.  Teams synchronise only among themselves (named barriers), so one
+// team's staging overlaps the other teams' arithmetic and the memory latency is decoupled from the
+// FMA loop.
+//
+// Inside a team 4 lanes own one row-block; a lane holds the 4 rows x 4 float4 columns accumulator
+// tile, so every 16-byte shared-memory read feeds R = 4 packed FMAs (FFMA2) and the per-step
+// broadcast reads (offset, weights) are amortised over 64 FMAs per lane.  The entry loop is software
+// pipelined by hand (offsets two steps ahead, weights and source values one step ahead).  The two
+// row-blocks that share a quarter-warp phase read opposite 64-byte halves of their rows (column
+// group XOR parity), which keeps the 128-bit reads bank-conflict free.
+// ---------------------------------------------------------------------------------------------
+constexpr int TEAM_THREADS = 128;   // 32 row-blocks x 4 lanes
+constexpr int MAX_TEAMS = 3;
+constexpr int PANEL_PAD = 4;        // zero entry steps appended so that the pipeline may over-read
+
+struct TeamHopPlan {
+  const int32_t* blkptr;
+  const int32_t* tp_ptr;
+  const float4* tp_val;
+  const uint32_t* tp_off;
+  const int32_t* tile_ptr;
+  const int32_t* tile_row;
+  int32_t n_blocks, n_rows, cap_len, cap_rows;
+  int32_t n_slabs;        // ceil(F / 64)
+  int32_t n_items;        // B * n_slabs
+  int32_t items_per_cta;
+  int32_t n_teams;
+};
+
+__device__ __forceinline__ void team_sync(int team) {
+  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(TEAM_THREADS) : "memory");
+}
+
+__device__ __forceinline__ void fma_step(float4 (&acc)[4][4], const float4& w, const float4 (&x)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    fma4(acc[0][j], w.x, x[j]);
+    fma4(acc[1][j], w.y, x[j]);
+    fma4(acc[2][j], w.z, x[j]);
+    fma4(acc[3][j], w.w, x[j]);
+  }
+}
+
+__global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1) hop_team_kernel(const TeamHopPlan P, const HopArgs a) {
+  extern __shared__ __align__(256) uint8_t tile_smem[];
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int blk0 = tile * DSW_TILE_BLOCKS;
+  const int t0 = __ldg(P.tp_ptr + tile);
+  const int len = __ldg(P.tp_ptr + tile + 1) - t0;
+  const int r0 = __ldg(P.tile_ptr + tile);
+  const int nrows = __ldg(P.tile_ptr + tile + 1) - r0;
+
+  // shared memory: [staged rows: n_teams x cap_rows x 256 B | weights | offsets | source-row ids]
+  const size_t xbuf_bytes = (size_t)P.cap_rows * 256;
+  const int cap_steps = P.cap_len + PANEL_PAD;
+  float4* s_val = reinterpret_cast<float4*>(tile_smem + (size_t)P.n_teams * xbuf_bytes);
+  uint32_t* s_off = reinterpret_cast<uint32_t*>(s_val + (size_t)cap_steps * DSW_TILE_BLOCKS);
+  int32_t* s_row = reinterpret_cast<int32_t*>(s_off + (size_t)cap_steps * DSW_TILE_BLOCKS);
+
+  {
+    const float4* gv = P.tp_val + (size_t)t0 * DSW_TILE_BLOCKS;
+    const uint32_t* go = P.tp_off + (size_t)t0 * DSW_TILE_BLOCKS;
+    const int n_real = len * DSW_TILE_BLOCKS, n_all = (len + PANEL_PAD) * DSW_TILE_BLOCKS;
+    for (int i = tid; i < n_all; i += blockDim.x) {
+      s_val[i] = i < n_real ? __ldg(gv + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s_off[i] = i < n_real ? __ldg(go + i) : 0u;
+    }
+    for (int i = tid; i < nrows; i += blockDim.x) s_row[i] = __ldg(P.tile_row + r0 + i);
+  }
+  __syncthreads();
+
+  const int team = tid / TEAM_THREADS;
+  if (team >= P.n_teams) return;
+  const int tt = tid - team * TEAM_THREADS;
+  const int slot = tt >> 2, l4 = tt & 3, par = slot & 1;
+  const int blk = blk0 + slot;
+  const bool active = blk < P.n_blocks;
+  int my_len = 0;
+  if (active) my_len = __ldg(P.blkptr + blk + 1) - __ldg(P.blkptr + blk);
+  // uniform trip count of the warp (8 row-blocks), rounded up to the 2-step pipeline
+  const int wlen = (__reduce_max_sync(0xffffffffu, my_len) + 1) & ~1;
+
+  uint8_t* xs = tile_smem + (size_t)team * xbuf_bytes;
+  const uint32_t xs_u32 = (uint32_t)__cvta_generic_to_shared(xs);
+  // byte offsets of this lane's float4 columns inside a staged row: j = 0/2 through cA, j = 1/3 through cB
+  const uint32_t cA = (uint32_t)(l4 * 16) ^ (uint32_t)(par * 64);
+  const uint32_t cB = (uint32_t)(l4 * 16 + 64) ^ (uint32_t)(par * 64);
+  const uint8_t* xA = xs + cA;
+  const uint8_t* xB = xs + cB;
+  const uint32_t* po = s_off + slot;
+  const float4* pw = s_val + slot;
+  // channel of accumulator column j inside the slab
+  int ch[4];
+  ch[0] = (int)(cA >> 2), ch[1] = (int)(cB >> 2), ch[2] = ch[0] + 32, ch[3] = ch[1] + 32;
+
+  const int item_begin = blockIdx.y * P.items_per_cta;
+  const int item_end = min(item_begin + P.items_per_cta, P.n_items);
+  for (int item = item_begin + team; item < item_end; item += P.n_teams) {
+    const int b = item / P.n_slabs, slab = item - b * P.n_slabs;
+    const int slab_f = min(64, a.F - slab * 64);       // channels in this slab (multiple of 4)
+    const int cpr = slab_f >> 2;                        // 16-byte chunks per row
+    // ---- stage the tile's source rows for this item ----
+    {
+      const float* xb = a.X + (int64_t)b * a.x_sB + slab * 64;
+      const int c = tt & 15;
+      if (c < cpr) {
+        const float* xc = xb + c * 4;
+        const uint32_t dc = xs_u32 + (uint32_t)c * 16u;
+#pragma unroll 4
+        for (int r = tt >> 4; r < nrows; r += TEAM_THREADS / 16) {
+          const float* src = xc + (int64_t)s_row[r] * a.x_sV;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dc + (uint32_t)r * 256u), "l"(src) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // Accumulators start at (beta * Z + G) / alpha (alpha is 1 or 2, so the scaling is exact): the
+    // loads are issued here, behind the cp.asyncs, and land while the tile is being staged.
+    float4 acc[4][4];
+    {
+      const float inv_alpha = 1.f / a.alpha;
+      const float zs = a.beta * inv_alpha;
+      bool ok[4][4];
+      int64_t eoff[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ok[r][j] = active && (blk * 4 + r) < P.n_rows && ch[j] < slab_f;
+          eoff[r][j] = (int64_t)slab * 64 + ch[j];
+        }
+      // batch 1: all Z loads in flight together
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.Z != nullptr && ok[r][j]) acc[r][j] = ldcg4(a.Z + b * a.z_sB + (int64_t)(blk * 4 + r) * a.z_sV + eoff[r][j]);
+        }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          acc[r][j] = make_float4(acc[r][j].x * zs, acc[r][j].y * zs, acc[r][j].z * zs, acc[r][j].w * zs);
+      // batch 2 (adjoint recurrence only): all G loads in flight together
+      if (a.G != nullptr) {
+        float4 g[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            g[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok[r][j]) g[r][j] = ldcg4(a.G + b * a.g_sB + (int64_t)(blk * 4 + r) * a.g_sV + eoff[r][j]);
+          }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            acc[r][j] = make_float4(fmaf(g[r][j].x, inv_alpha, acc[r][j].x), fmaf(g[r][j].y, inv_alpha, acc[r][j].y),
+                                    fmaf(g[r][j].z, inv_alpha, acc[r][j].z), fmaf(g[r][j].w, inv_alpha, acc[r][j].w));
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    team_sync(team);
+
+    {
+      auto load_x = [&](uint32_t o, float4(&x)[4]) {
+        x[0] = *reinterpret_cast<const float4*>(xA + o);
+        x[1] = *reinterpret_cast<const float4*>(xB + o);
+        x[2] = *reinterpret_cast<const float4*>(xA + o + 128);
+        x[3] = *reinterpret_cast<const float4*>(xB + o + 128);
+      };
+      // software pipeline: offsets two steps ahead, weights / values one step ahead; the panels carry
+      // PANEL_PAD zero steps so the over-reads at the tail are harmless.
+      float4 x0[4], x1[4], w0, w1;
+      uint32_t o1, o2;
+      w0 = pw[0];
+      load_x(po[0], x0);
+      o1 = po[DSW_TILE_BLOCKS];
+#pragma unroll 1
+      for (int u = 0; u < wlen; u += 2) {
+        w1 = pw[(u + 1) * DSW_TILE_BLOCKS];
+        load_x(o1, x1);
+        o2 = po[(u + 2) * DSW_TILE_BLOCKS];
+        fma_step(acc, w0, x0);
+        w0 = pw[(u + 2) * DSW_TILE_BLOCKS];
+        load_x(o2, x0);
+        o1 = po[(u + 3) * DSW_TILE_BLOCKS];
+        fma_step(acc, w1, x1);
+      }
+    }
+
+    // ---- epilogue: O = alpha * acc ----
+    if (active) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int row = blk * 4 + r;
+        if (row >= P.n_rows) break;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (ch[j] >= slab_f) continue;
+          const int64_t col = (int64_t)slab * 64 + ch[j];
+          *reinterpret_cast<float4*>(a.O + b * a.o_sB + row * a.o_sV + col) =
+              make_float4(a.alpha * acc[r][j].x, a.alpha * acc[r][j].y, a.alpha * acc[r][j].z, a.alpha * acc[r][j].w);
+        }
+      }
+    }
+    // every lane of the team is done reading the staged rows before the next item overwrites them
+    team_sync(team);
+  }
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static bool vec4_ok(const HopArgs& a) {
@@ -175,7 +518,62 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
   if (a.B <= 0 || a.F <= 0 || !a.X || !a.O) return DSW_ERR_BAD_ARGUMENT;
   if (a.B > 65535) return DSW_ERR_UNSUPPORTED;
   const bool v4 = vec4_ok(a);
-  if (v4 && rb.R > 0) {
+  const int hop_mode = (int)g_options[DSW_OPT_HOP_KERNEL].load(std::memory_order_relaxed);
+  // 32-bit byte offsets inside one sample: (n_cols - 1) * x_sV * 4 + F * 4 must fit
+  const bool off32 = ((int64_t)A.n_cols * a.x_sV + a.F) * 4 < ((int64_t)1 << 32);
+  if (v4 && rb.R == 4 && hop_mode == 0 && rb.n_tiles > 0) {
+    const size_t panels = (size_t)(rb.tile_len_max + PANEL_PAD) * DSW_TILE_BLOCKS * 20 + (size_t)rb.tile_rows_max * 4 + 64;
+    const size_t xbuf = (size_t)rb.tile_rows_max * 256;
+    int n_teams = panels < 200 * 1024 ? (int)std::min<size_t>(MAX_TEAMS, (226 * 1024 - panels) / std::max<size_t>(xbuf, 1)) : 0;
+    if (n_teams >= 1) {
+      TeamHopPlan P{};
+      P.blkptr = rb.blkptr, P.tp_ptr = rb.tp_ptr, P.tp_val = rb.tp_val, P.tp_off = rb.tp_off;
+      P.tile_ptr = rb.tile_ptr, P.tile_row = rb.tile_row;
+      P.n_blocks = rb.n_blocks, P.n_rows = A.n_rows, P.cap_len = rb.tile_len_max, P.cap_rows = rb.tile_rows_max;
+      P.n_slabs = ceil_div(a.F, 64);
+      P.n_items = a.B * P.n_slabs;
+      n_teams = std::min(n_teams, P.n_items);
+      P.n_teams = n_teams;
+      // items per CTA: a few per team to amortise the staged panels, while keeping >= ~3 waves of CTAs
+      int ipc = n_teams;
+      while (ipc < 4 * n_teams && ipc * 2 <= P.n_items && (int64_t)rb.n_tiles * ceil_div(P.n_items, ipc * 2) >= 148 * 3)
+        ipc *= 2;
+      P.items_per_cta = ipc;
+      const size_t smem = (size_t)n_teams * xbuf + panels;
+      dim3 grid(rb.n_tiles, ceil_div(P.n_items, ipc));
+      static std::atomic<bool> attr_set{false};
+      if (!attr_set.exchange(true))
+        DSW_CUDA_TRY(cudaFuncSetAttribute(hop_team_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      hop_team_kernel<<<grid, TEAM_THREADS * MAX_TEAMS, smem, st>>>(P, a);
+      return check_launch();
+    }
+  }
+  if (v4 && rb.R == 4 && hop_mode == 3 && off32 && rb.tile_entries_max > 0) {
+    const size_t smem = (size_t)((rb.tile_entries_max + 3) & ~3) * 20;
+    const int n_tiles = ceil_div(rb.n_blocks, TILE_BLOCKS);
+    if (smem <= 200 * 1024) {
+      const int nf = a.F > 32 ? 2 : 1;
+      const int slabs = ceil_div(a.F, 32 * nf);
+      // samples per CTA: amortise the staged panels while keeping >= ~6 CTAs per SM in the grid
+      int ns = 1;
+      while (ns < 8 && ns * 2 <= a.B && (int64_t)n_tiles * slabs * ceil_div(a.B, ns * 2) >= 148 * 6) ns *= 2;
+      dim3 grid(n_tiles, slabs, ceil_div(a.B, ns));
+      static std::atomic<bool> attr_set[2] = {{false}, {false}};
+      if (nf == 2) {
+        if (smem > 48 * 1024 && !attr_set[1].exchange(true))
+          DSW_CUDA_TRY(cudaFuncSetAttribute(hop_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        hop_tile_kernel<2><<<grid, TILE_THREADS, smem, st>>>(rb.blkptr, rb.ucol, reinterpret_cast<const float4*>(rb.uval),
+                                                             rb.n_blocks, A.n_rows, ns, a);
+      } else {
+        if (smem > 48 * 1024 && !attr_set[0].exchange(true))
+          DSW_CUDA_TRY(cudaFuncSetAttribute(hop_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        hop_tile_kernel<1><<<grid, TILE_THREADS, smem, st>>>(rb.blkptr, rb.ucol, reinterpret_cast<const float4*>(rb.uval),
+                                                             rb.n_blocks, A.n_rows, ns, a);
+      }
+      return check_launch();
+    }
+  }
+  if (v4 && rb.R > 0 && hop_mode <= 1) {
     const int threads = 512;
     const int slots = threads / 16;
     dim3 grid(ceil_div(rb.n_blocks, slots), ceil_div(a.F, 64), a.B);
@@ -222,34 +620,6 @@ int dsw_spmm_bwd(const dsw_plan* mat, const float* dy, int64_t dy_sB, int64_t dy
   a.O = dx, a.o_sV = F, a.o_sB = (int64_t)mat->tr.n_rows * F;
   a.B = B, a.F = F;
   return launch_hop(mat->tr, mat->tr_rb, a, static_cast<cudaStream_t>(stream));
-}
-
-int dsw_cheb_terms(const dsw_plan* lap, const float* x, int64_t x_sB, int64_t x_sV, float* terms, int32_t B,
-                   int32_t F, int32_t K, void* stream) {
-  if (!lap || !x || B <= 0 || F <= 0 || K < 1) return DSW_ERR_BAD_ARGUMENT;
-  if (K > DSW_MAX_K) return DSW_ERR_UNSUPPORTED;
-  if (lap->fwd.n_rows != lap->fwd.n_cols) return DSW_ERR_SHAPE;
-  if (K > 1 && !terms) return DSW_ERR_BAD_ARGUMENT;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int64_t V = lap->fwd.n_rows, plane = (int64_t)B * V * F;
-  for (int k = 1; k < K; ++k) {
-    HopArgs a;
-    a.B = B, a.F = F;
-    a.O = terms + (k - 1) * plane, a.o_sB = V * F, a.o_sV = F;
-    if (k == 1) {
-      a.X = x, a.x_sB = x_sB, a.x_sV = x_sV;
-    } else {
-      a.X = terms + (k - 2) * plane, a.x_sB = V * F, a.x_sV = F;
-      a.alpha = 2.f, a.beta = -1.f;
-      if (k == 2) {
-        a.Z = x, a.z_sB = x_sB, a.z_sV = x_sV;
-      } else {
-        a.Z = terms + (k - 3) * plane, a.z_sB = V * F, a.z_sV = F;
-      }
-    }
-    DSW_TRY(launch_hop(lap->fwd, lap->fwd_rb, a, st));
-  }
-  return DSW_OK;
 }
 
 }  // extern "C"

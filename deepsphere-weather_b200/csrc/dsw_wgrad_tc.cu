@@ -375,12 +375,17 @@ static void wgrad_tc_geometry(int64_t N, int32_t K, int32_t Fin, int32_t Fout, i
   nsplit = (int)((total_kb + kb_per_split - 1) / kb_per_split);
 }
 
-size_t wgrad_tc_partial_bytes(int64_t N, int32_t K, int32_t Fin, int32_t Fout) {
+int wgrad_tc_nsplit(int64_t N, int32_t K, int32_t Fin, int32_t Fout) {
   int BN, ntiles, mtiles, nsplit, kbps;
   wgrad_tc_geometry(N, K, Fin, Fout, BN, ntiles, mtiles, nsplit, kbps);
-  return (size_t)nsplit * ((size_t)K * Fin + 1) * Fout * sizeof(float);
+  return nsplit;
 }
 
+size_t wgrad_tc_partial_bytes(int64_t N, int32_t K, int32_t Fin, int32_t Fout) {
+  return (size_t)wgrad_tc_nsplit(N, K, Fin, Fout) * ((size_t)K * Fin + 1) * Fout * sizeof(float);
+}
+
+// Writes wgrad_tc_nsplit() partials at a.partial; the caller sums them with launch_wgrad_reduce.
 int launch_wgrad_tc(const WgradArgs& a, size_t partial_bytes, cudaStream_t st) {
   if (!a.partial) return DSW_ERR_UNSUPPORTED;
   if (partial_bytes < wgrad_tc_partial_bytes(a.N, a.K, a.Fin, a.Fout)) return DSW_ERR_UNSUPPORTED;
@@ -403,8 +408,7 @@ int launch_wgrad_tc(const WgradArgs& a, size_t partial_bytes, cudaStream_t st) {
                                       (int)wtc::smem_bytes_for(4)));  // + 1 KB static bias_acc <= 227 KB
   dim3 grid(mtiles, ntiles, nsplit);
   wtc::wgrad_tc_kernel<<<grid, wtc::THREADS, smem, st>>>(P);
-  DSW_TRY(check_launch());
-  return launch_wgrad_reduce(a.partial, nsplit, a.K, a.Fin, a.Fout, a.dW, a.dbias, st);
+  return check_launch();
 }
 
 }  // namespace dsw

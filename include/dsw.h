@@ -174,6 +174,16 @@ int64_t dsw_launch_count(void);
 /* 0 = fp32 CUDA-core channel mix, 1 = tcgen05 split-bf16 (3-term) channel mix when shapes allow. */
 int dsw_set_mix_mode(int mode);
 int dsw_get_mix_mode(void);
+/* Tuning / A-B switches (process-wide; defaults are what production uses).  Values are >= 0. */
+enum {
+  DSW_OPT_HOP_KERNEL = 0,    /* 0 = auto (bulk-copy-staged tile kernel), 1 = row-block kernel through L1, 2 = plain CSR, 3 = panel-staged L1 tile kernel */
+  DSW_OPT_L2_CHUNK_BYTES = 1, /* working-set budget (bytes) of L2-resident sample chunks; 0 / 1 = chunking off (default) */
+  DSW_OPT_RESERVED2 = 2,
+  DSW_OPT_RESERVED3 = 3,
+  DSW_OPT_COUNT = 4
+};
+int dsw_set_option(int key, int64_t value);
+int64_t dsw_get_option(int key);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,10 @@ def main():
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
+    from deepsphere_weather_b200 import _lib
+    lib = _lib.load()
+    lib.dsw_set_option(0, int(os.environ.get("DSW_HOP", "0")))
+    lib.dsw_set_option(1, int(os.environ.get("DSW_CHUNK", "0")))
     if what == "unet":
         model, V = bench.build_model(dev)
         x = torch.randn(bench.BATCH_PER_GPU, 3, V, 7, device=dev)
