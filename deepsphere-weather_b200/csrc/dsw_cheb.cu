@@ -209,8 +209,8 @@ size_t dsw_cheb_bwd_weight_workspace_bytes(int32_t B, int32_t V, int32_t Fin, in
 }
 
 int dsw_cheb_bwd_weight(const dsw_plan* lap, const float* x, int64_t x_sB, int64_t x_sV, const float* dy,
-                        float* dW, float* dbias, int32_t B, int32_t Fin, int32_t Fout, int32_t K,
-                        void* workspace, size_t workspace_bytes, void* stream) {
+                        const float* saved_terms, float* dW, float* dbias, int32_t B, int32_t Fin, int32_t Fout,
+                        int32_t K, void* workspace, size_t workspace_bytes, void* stream) {
   DSW_TRY(check_common(lap, B, Fin, Fout, K));
   if (!x || !dy || !dW) return DSW_ERR_BAD_ARGUMENT;
   const int32_t V = lap->fwd.n_rows;
@@ -218,7 +218,8 @@ int dsw_cheb_bwd_weight(const dsw_plan* lap, const float* x, int64_t x_sB, int64
     return DSW_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const WgradPlan p = wgrad_plan(B, V, Fin, Fout, K);
-  float* terms = static_cast<float*>(workspace);
+  if (saved_terms && p.nchunks != 1) return DSW_ERR_UNSUPPORTED;  // saved terms need the unchunked layout
+  float* terms = saved_terms ? const_cast<float*>(saved_terms) : static_cast<float*>(workspace);
   float* partial = reinterpret_cast<float*>(static_cast<char*>(workspace) + p.terms_bytes);
   const int64_t plane = (int64_t)p.Bc * V * Fin;
   const int64_t part_floats = (int64_t)(p.part_bytes / sizeof(float));
@@ -226,7 +227,7 @@ int dsw_cheb_bwd_weight(const dsw_plan* lap, const float* x, int64_t x_sB, int64
   for (int32_t c = 0; c < p.nchunks; ++c) {
     const int32_t b0 = c * p.Bc;
     const float* xc = x + b0 * x_sB;
-    DSW_TRY(run_terms(lap, xc, x_sB, x_sV, terms, plane, p.Bc, Fin, K, st));
+    if (!saved_terms) DSW_TRY(run_terms(lap, xc, x_sB, x_sV, terms, plane, p.Bc, Fin, K, st));
     WgradArgs w;
     w.K = K, w.Fin = Fin, w.Fout = Fout, w.rows_per_batch = V, w.N = (int64_t)p.Bc * V;
     w.T[0] = xc, w.t_sB[0] = x_sB, w.t_sV[0] = x_sV;

@@ -7,6 +7,7 @@ bookkeeping.  Non-CUDA tensors raise (no CPU fallback).
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 
 import torch
@@ -36,6 +37,18 @@ def _channel_last(x: torch.Tensor) -> torch.Tensor:
     if x.shape[2] == 1 and x.stride(2) != 1:
         return x.contiguous()
     return x
+
+
+# Keep the forward's Chebyshev terms for the weight gradient (what the reference's autograd does
+# too) instead of recomputing them: one third fewer SpMM hops per step for (K-1)/K of an activation
+# of extra memory per layer.  DSW_SAVE_TERMS=0 (or set_save_terms(False)) recomputes.
+_SAVE_TERMS = os.environ.get("DSW_SAVE_TERMS", "1") != "0"
+_OPT_L2_CHUNK = 1
+
+
+def set_save_terms(flag: bool) -> None:
+    global _SAVE_TERMS
+    _SAVE_TERMS = bool(flag)
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
@@ -144,7 +157,9 @@ class ChebConvFunction(torch.autograd.Function):
         _lib.check(rc, "dsw_cheb_fwd")
         # Only x and W are saved: callers modify our output in place (`x_out *= rezero_weight`,
         # my_models_graph.py:213), so the backward recomputes the Chebyshev terms instead.
-        ctx.save_for_backward(x, w)
+        keep = _SAVE_TERMS and K > 1 and lib.dsw_get_option(_OPT_L2_CHUNK) <= 1 and (
+            ctx.needs_input_grad[1] or (bias is not None and ctx.needs_input_grad[2]))
+        ctx.save_for_backward(x, w, *([ws] if keep else []))
         ctx.plan = plan
         ctx.has_bias = bias is not None
         return y
@@ -152,7 +167,8 @@ class ChebConvFunction(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        x, w = ctx.saved_tensors
+        x, w, *saved = ctx.saved_tensors
+        terms_ptr = saved[0].data_ptr() if saved else None
         plan = ctx.plan
         lib = _lib.load()
         B, V, Fin = x.shape
@@ -174,7 +190,7 @@ class ChebConvFunction(torch.autograd.Function):
                 db = torch.empty(Fout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
                 ws = _workspace(lib.dsw_cheb_bwd_weight_workspace_bytes(B, V, Fin, Fout, K), x.device)
                 rc = lib.dsw_cheb_bwd_weight(
-                    plan.handle, x.data_ptr(), x.stride(0), x.stride(1), dy.data_ptr(), dw.data_ptr(),
+                    plan.handle, x.data_ptr(), x.stride(0), x.stride(1), dy.data_ptr(), terms_ptr, dw.data_ptr(),
                     db.data_ptr() if db is not None else None, B, Fin, Fout, K,
                     ws.data_ptr(), ws.numel(), st,
                 )

@@ -102,12 +102,14 @@ int dsw_cheb_bwd_data(const dsw_plan* lap, const float* dy, const float* W, floa
 
 /* Gradient w.r.t. weight and bias (autograd of layers.py:176-177 and :375):
  *     dW[f,k,o] = sum_{b,v} (T_k(L) x_b)[v,f] dy[b,v,o],   dbias[o] = sum_{b,v} dy[b,v,o]
- * The Chebyshev terms are recomputed (they are not saved by the forward).  dW is overwritten
+ * `saved_terms` = the [K-1][B][V][Fin] Chebyshev terms the forward left at the start of its workspace
+ * (valid when sample chunking is off), or NULL to recompute them here (the forward then need not keep
+ * its workspace; the reference itself keeps every term alive for autograd).  dW is overwritten
  * ([Fin][K][Fout]); dbias may be NULL.  Deterministic (fixed-order two-pass reduction). */
 size_t dsw_cheb_bwd_weight_workspace_bytes(int32_t B, int32_t V, int32_t Fin, int32_t Fout, int32_t K);
 int dsw_cheb_bwd_weight(const dsw_plan* lap, const float* x, int64_t x_sB, int64_t x_sV,
-                        const float* dy, float* dW, float* dbias, int32_t B, int32_t Fin,
-                        int32_t Fout, int32_t K, void* workspace, size_t workspace_bytes,
+                        const float* dy, const float* saved_terms, float* dW, float* dbias, int32_t B,
+                        int32_t Fin, int32_t Fout, int32_t K, void* workspace, size_t workspace_bytes,
                         void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -93,6 +93,52 @@ def test_convcheb_matches_oracle_seeded(B, nside, Fin, Fout, K, dev, mix_mode):
     assert rel_err(layer.bias.grad, bo.grad) < REL_TOL
 
 
+@pytest.mark.parametrize("hop_kernel", [0, 1, 2, 3], ids=["hop-team", "hop-rb", "hop-csr", "hop-l1tile"])
+@pytest.mark.parametrize("chunk_bytes", [0, 1 << 20], ids=["nochunk", "chunk1MB"])
+@pytest.mark.parametrize("save_terms", [True, False], ids=["saved-terms", "recompute"])
+def test_hop_kernels_chunking_and_saved_terms_agree(hop_kernel, chunk_bytes, save_terms, dev, lib):
+    """Every hop kernel variant, the L2-resident sample chunking and the saved-terms / recompute
+    weight-gradient paths are the same arithmetic: all must match the oracle."""
+    from deepsphere_weather_b200 import functional as F_
+    from deepsphere_weather_b200 import graphs as G
+    from deepsphere_weather_b200 import layers as L
+    from oracle import cheb_oracle as O
+
+    torch.manual_seed(7)
+    lap = G.healpix_laplacian(8)  # 768 nodes = 6 tiles of 128 rows
+    V, B, Fin, Fout, K = lap.shape[0], 6, 96, 40, 5  # a partial second slab (96 = 64 + 32)
+    x, dy = torch.randn(B, V, Fin), torch.randn(B, V, Fout)
+    w, b = torch.randn(Fin, K, Fout) * 0.05, torch.randn(Fout) * 0.1
+    xo, wo, bo = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yo = O.conv_cheb_layer(lap, xo, wo, bo)
+    yo.backward(dy)
+    lib.dsw_set_option(0, hop_kernel)
+    lib.dsw_set_option(1, chunk_bytes)
+    F_.set_save_terms(save_terms)
+    try:
+        layer = L.ConvCheb(Fin, Fout, K, lap).to(dev)
+        layer.set_parameters(w.to(dev), b.to(dev))
+        xg = x.to(dev).requires_grad_(True)
+        yg = layer(xg)
+        yg.backward(dy.to(dev))
+        assert rel_err(yg, yo) < REL_TOL
+        assert rel_err(xg.grad, xo.grad) < REL_TOL
+        assert rel_err(layer.weight.grad, wo.grad) < REL_TOL
+        assert rel_err(layer.bias.grad, bo.grad) < REL_TOL
+        # the recurrence alone (layers.py:163-169), restated with torch.sparse.mm on the CPU
+        terms = F_.cheb_terms(x.to(dev), F_.plan_for(lap.to(dev)), K)
+        x0 = x.permute(1, 2, 0).reshape(V, Fin * B)
+        t = [x0, torch.sparse.mm(lap, x0)]
+        for _ in range(2, K):
+            t.append(2 * torch.sparse.mm(lap, t[-1]) - t[-2])
+        for k in range(1, K):
+            assert rel_err(terms[k - 1], t[k].reshape(V, Fin, B).permute(2, 0, 1)) < REL_TOL
+    finally:
+        lib.dsw_set_option(0, 0)
+        lib.dsw_set_option(1, 0)
+        F_.set_save_terms(True)
+
+
 def test_convcheb_accepts_strided_views(dev):
     """Pool outputs of the reference are [V',F,B]-ordered views (layers.py:963); any strides must work."""
     from deepsphere_weather_b200 import graphs as G
