@@ -17,6 +17,7 @@
 // Two-stage ring per CTA; with BN <= 64 two CTAs share an SM so one CTA's epilogue overlaps the other's
 // main loop.  B (the weights) is split and laid out as ready-to-copy shared-memory images by a small
 // prep kernel once per call.
+#include <cuda.h>
 #include <cuda_bf16.h>
 
 #include <algorithm>
@@ -29,9 +30,6 @@ namespace tc {
 constexpr int BM = 128;          // UMMA M (cta_group::1)
 constexpr int BKB = 64;          // reduction elements per stage: 64 bf16 = one 128-byte swizzle row
 constexpr int A_TILE = BM * 128; // bytes of one bf16 A image (hi or lo)
-constexpr int CONV_THREADS = 256;
-constexpr int THREADS = CONV_THREADS + 32;
-constexpr int STAGES = 2;
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -118,6 +116,15 @@ __device__ __host__ __forceinline__ uint32_t swz(uint32_t row, uint32_t chunk) {
   return row * 128u + (((chunk ^ (row & 7u)) & 7u) << 4);
 }
 
+// streaming 16-byte load that does not allocate an L1 line (the A operand is read exactly once)
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(v);
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));
@@ -131,7 +138,9 @@ struct TcArgs {
   const uint8_t* bprep;  // [n_tiles][P * nkb][hi image | lo image], image = BN x 128 B swizzled
   int32_t BN;            // columns per CTA (multiple of 16, <= 256)
   int32_t nkb;           // 64-wide reduction blocks per plane
-  int32_t tmem_cols;     // power of two >= max(32, BN)
+  int32_t tmem_cols;     // power of two >= max(32, BN); two accumulators are allocated
+  int32_t stages;        // shared-memory ring depth
+  int32_t n_ctiles;      // column tiles
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -174,62 +183,92 @@ __global__ void __launch_bounds__(256) mix_tc_prep_kernel(TcArgs P, uint8_t* __r
 }
 
 // ---------------------------------------------------------------------------------------------
-// main kernel
+// main kernel: persistent, warp-specialised
+//
+//   warps 0-7   converters   fp32 A rows (global, coalesced float4, one 64-wide reduction block kept in
+//                            flight in registers) -> bf16 hi / lo -> shared memory stage (UMMA K-major
+//                            SWIZZLE_128B); arrive on a_full[stage]
+//   warp  8     B loader     one lane: cp.async.bulk of the pre-split weight block [hi | lo] into the
+//                            stage, completion (tx bytes) on b_full[stage]
+//   warp  9     MMA issuer   one lane: 3 x tcgen05.mma per 16-wide K step into the TMEM accumulator of
+//                            the current tile (two accumulators, ping-pong); tcgen05.commit releases the
+//                            stage (empty[stage]) and, after a tile's last block, hands the accumulator
+//                            to the epilogue (acc_full[buf])
+//   warps 10-13 epilogue     tcgen05.ld -> + bias / ReLU -> global; arrive on acc_empty[buf]
+//
+// CTAs are persistent (grid = #SMs) and walk the (row tile, column tile) list with a static stride, so
+// barrier / TMEM set-up happens once and the converters stream straight across tile boundaries while
+// the epilogue of the previous tile drains the other accumulator.
 // ---------------------------------------------------------------------------------------------
+constexpr int N_CONV_WARPS = 8;
+constexpr int WARP_BLOAD = 8, WARP_MMA = 9, WARP_EPI0 = 10;
+constexpr int THREADS2 = 32 * 14;
+
 template <bool VEC4>
-__global__ void __launch_bounds__(THREADS, 1) mix_tc_kernel(const __grid_constant__ TcArgs P) {
+__global__ void __launch_bounds__(THREADS2, 1) mix_tc_kernel(const __grid_constant__ TcArgs P) {
   extern __shared__ uint8_t smem_raw[];
   const MixArgs& a = P.m;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int BN = P.BN;
+  const int S = P.stages;
   const uint32_t b_img = (uint32_t)BN * 128u;
   const uint32_t stage_bytes = 2u * A_TILE + 2u * b_img;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bars = smem_base + STAGES * stage_bytes;
-  // barrier slots (8 bytes each): a_full[2], b_full[2], empty[2]; then the TMEM address slot
+  const uint32_t bars = smem_base + (uint32_t)S * stage_bytes;
+  // barrier slots (8 bytes each): a_full[S], b_full[S], empty[S], acc_full[2], acc_empty[2]; then the TMEM slot
   auto a_full = [&](int s) { return bars + 8u * s; };
-  auto b_full = [&](int s) { return bars + 16u + 8u * s; };
-  auto empty = [&](int s) { return bars + 32u + 8u * s; };
-  const uint32_t tmem_slot = bars + 48u;
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * stage_bytes + 48);
+  auto b_full = [&](int s) { return bars + 8u * (S + s); };
+  auto empty = [&](int s) { return bars + 8u * (2 * S + s); };
+  auto acc_full = [&](int b) { return bars + 8u * (3 * S + b); };
+  auto acc_empty = [&](int b) { return bars + 8u * (3 * S + 2 + b); };
+  const uint32_t tmem_slot = bars + 8u * (3 * S + 4);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (size_t)S * stage_bytes + 8 * (3 * S + 4));
 
   if (t == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(a_full(s), CONV_THREADS);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(a_full(s), N_CONV_WARPS * 32);
       mbar_init(b_full(s), 1);
       mbar_init(empty(s), 1);
     }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), 128);
+    }
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+  if (warp == WARP_MMA) tmem_alloc(tmem_slot, (uint32_t)(2 * P.tmem_cols));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  const int64_t n0 = (int64_t)blockIdx.x * BM;
-  const int tile = blockIdx.y;
   const int total_kb = a.P * P.nkb;
   const int last_ksteps = (a.Ka - (P.nkb - 1) * BKB + 15) / 16;  // K-steps (of 16) in a plane's last block
+  const int n_ctiles = P.n_ctiles;
+  const int64_t n_rtiles = (a.N + BM - 1) / BM;
+  const int64_t n_tiles = n_rtiles * n_ctiles;
 
-  if (warp < 8) {
+  if (warp < N_CONV_WARPS) {
     // ================= converters =================
     // thread -> rows (t>>4) + 16*i, i = 0..7; float4 column q = t & 15 (reduction elements 4q..4q+3)
     const int q = t & 15;
+    float4 cur[8];
     int32_t rb[8], rv[8];
     bool rok[8];
+    auto set_rows = [&](int64_t tile) {
+      const int64_t n0 = (tile / n_ctiles) * BM;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int64_t n = n0 + (t >> 4) + 16 * i;
-      rok[i] = n < a.N;
-      const int64_t bb = rok[i] ? n / a.rows_per_batch : 0;
-      rb[i] = (int32_t)bb;
-      rv[i] = rok[i] ? (int32_t)(n - bb * a.rows_per_batch) : 0;
-    }
-    float4 cur[8];
-    auto load_block = [&](int kbi, float4 (&dst)[8]) {
+      for (int i = 0; i < 8; ++i) {
+        const int64_t n = n0 + (t >> 4) + 16 * i;
+        rok[i] = n < a.N;
+        const int64_t bb = rok[i] ? n / a.rows_per_batch : 0;
+        rb[i] = (int32_t)bb;
+        rv[i] = rok[i] ? (int32_t)(n - bb * a.rows_per_batch) : 0;
+      }
+    };
+    auto load_block = [&](int kbi, float4(&dst)[8]) {
       const int p = kbi / P.nkb, kb = kbi - p * P.nkb;
       const int kk = kb * BKB + q * 4;
       const float* __restrict__ Ap = a.A[p];
@@ -240,7 +279,7 @@ __global__ void __launch_bounds__(THREADS, 1) mix_tc_kernel(const __grid_constan
         if (rok[i]) {
           const float* src = Ap + rb[i] * sB + rv[i] * sV + kk;
           if (VEC4) {
-            if (kk < a.Ka) v = __ldg(reinterpret_cast<const float4*>(src));  // Ka % 4 == 0
+            if (kk < a.Ka) v = ld_stream4(src);  // Ka % 4 == 0; streamed once
           } else {
             if (kk + 0 < a.Ka) v.x = __ldg(src + 0);
             if (kk + 1 < a.Ka) v.y = __ldg(src + 1);
@@ -251,106 +290,477 @@ __global__ void __launch_bounds__(THREADS, 1) mix_tc_kernel(const __grid_constan
         dst[i] = v;
       }
     };
-    load_block(0, cur);
-    for (int kbi = 0; kbi < total_kb; ++kbi) {
-      const int s = kbi & 1;
-      if (kbi >= STAGES) {
-        mbar_wait(empty(s), ((kbi >> 1) - 1) & 1);
-        tc_fence_after();
-      }
-      uint8_t* Ahi = smem_gen + s * stage_bytes;
+    // Two 64-wide blocks are kept in flight per thread (64 KB per SM): (tile, block) pairs are walked
+    // as one flat sequence, so the prefetch runs straight across tile boundaries.
+    float4 nxt[8];
+    int64_t ld_tile = blockIdx.x;  // position of the next block to *load*
+    int ld_kbi = 0;
+    auto advance_load = [&](float4(&dst)[8]) {
+      if (ld_tile >= n_tiles) return;
+      if (ld_kbi == 0) set_rows(ld_tile);
+      load_block(ld_kbi, dst);
+      if (++ld_kbi == total_kb) ld_kbi = 0, ld_tile += gridDim.x;
+    };
+    advance_load(cur);
+    advance_load(nxt);
+    auto convert_store = [&](int s, const float4(&src)[8]) {
+      uint8_t* Ahi = smem_gen + (size_t)s * stage_bytes;
       uint8_t* Alo = Ahi + A_TILE;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const uint32_t row = (t >> 4) + 16 * i;
         __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-        split_bf16(cur[i].x, h0, l0);
-        split_bf16(cur[i].y, h1, l1);
-        split_bf16(cur[i].z, h2, l2);
-        split_bf16(cur[i].w, h3, l3);
+        split_bf16(src[i].x, h0, l0);
+        split_bf16(src[i].y, h1, l1);
+        split_bf16(src[i].z, h2, l2);
+        split_bf16(src[i].w, h3, l3);
         const uint32_t off = swz(row, q >> 1) + (q & 1) * 8;
         *reinterpret_cast<uint2*>(Ahi + off) = make_uint2(pack2(h0, h1), pack2(h2, h3));
         *reinterpret_cast<uint2*>(Alo + off) = make_uint2(pack2(l0, l1), pack2(l2, l3));
       }
-      if (kbi + 1 < total_kb) load_block(kbi + 1, cur);  // in flight while the MMAs of this block run
-      fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
-      mbar_arrive(a_full(s));
+    };
+    const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const int64_t n_iters = my_tiles * total_kb;
+    for (int64_t it2 = 0; it2 < n_iters; it2 += 2) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int64_t itx = it2 + half;
+        if (itx >= n_iters) break;
+        const int s = (int)(itx % S);
+        const uint32_t use = (uint32_t)(itx / S);  // how many times this stage has been filled before
+        if (use > 0) {
+          mbar_wait(empty(s), (use - 1) & 1);
+          tc_fence_after();
+        }
+        if (half == 0) {
+          convert_store(s, cur);
+          advance_load(cur);
+        } else {
+          convert_store(s, nxt);
+          advance_load(nxt);
+        }
+        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive(a_full(s));
+      }
     }
-    // ================= epilogue =================
-    {
-      const int last = total_kb - 1;
-      mbar_wait(empty(last & 1), (last >> 1) & 1);
-      tc_fence_after();
+  } else if (warp == WARP_BLOAD) {
+    // ================= B loader (one thread) =================
+    if (lane == 0) {
+      int64_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int ctile = (int)(tile % n_ctiles);
+        const uint8_t* bsrc = P.bprep + (int64_t)ctile * total_kb * 2 * b_img;
+        for (int kbi = 0; kbi < total_kb; ++kbi, ++it) {
+          const int s = (int)(it % S);
+          const uint32_t use = (uint32_t)(it / S);
+          if (use > 0) mbar_wait(empty(s), (use - 1) & 1);
+          mbar_expect_tx(b_full(s), 2u * b_img);
+          bulk_copy_g2s(smem_base + s * stage_bytes + 2u * A_TILE, bsrc + (int64_t)kbi * 2 * b_img, 2u * b_img, b_full(s));
+        }
+      }
     }
-    const int quarter = warp & 3;                   // TMEM lanes 32*quarter .. +31
-    const int half = warp >> 2;                     // column half handled by this warp
-    const int64_t n = n0 + quarter * 32 + lane;     // output row of this thread
-    const int chunks = BN / 16;
-    const int c_begin = (chunks * half) / 2, c_end = (chunks * (half + 1)) / 2;
+  } else if (warp == WARP_MMA) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int64_t it = 0;
+      int64_t local_tile = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local_tile) {
+        const int buf = (int)(local_tile & 1);
+        const uint32_t buse = (uint32_t)(local_tile >> 1);
+        if (buse > 0) {
+          mbar_wait(acc_empty(buf), (buse - 1) & 1);
+          tc_fence_after();
+        }
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * P.tmem_cols);
+        for (int kbi = 0; kbi < total_kb; ++kbi, ++it) {
+          const int s = (int)(it % S);
+          const uint32_t ph = (uint32_t)(it / S) & 1;
+          mbar_wait(a_full(s), ph);
+          mbar_wait(b_full(s), ph);
+          tc_fence_after();
+          const uint32_t st_base = smem_base + s * stage_bytes;
+          const int kb = kbi % P.nkb;
+          const int ksteps = (kb == P.nkb - 1) ? last_ksteps : BKB / 16;
+          const uint64_t dAh = make_desc(st_base), dAl = make_desc(st_base + A_TILE);
+          const uint64_t dBh = make_desc(st_base + 2u * A_TILE), dBl = make_desc(st_base + 2u * A_TILE + b_img);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t adv = (uint64_t)(ks * 2);  // 32 bytes per K-step, in 16-byte units
+            umma_bf16(d_tmem, dAh + adv, dBh + adv, idesc, (kbi | ks) != 0);
+            umma_bf16(d_tmem, dAh + adv, dBl + adv, idesc, 1u);
+            umma_bf16(d_tmem, dAl + adv, dBh + adv, idesc, 1u);
+          }
+          umma_commit(empty(s));  // arrives when every MMA issued so far has completed
+        }
+        umma_commit(acc_full(buf));
+      }
+    }
+  } else {
+    // ================= epilogue (4 warps = the 4 TMEM lane quarters) =================
+    const int quarter = warp & 3;  // tcgen05.ld: a warp reads lanes 32*(warp%4) .. +31
     const bool vec_store = (a.Cw % 4 == 0) && (a.ldc % 4 == 0) && (a.sCp % 4 == 0) &&
                            ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0);
-    for (int ch = c_begin; ch < c_end; ++ch) {
-      uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 16), r);
-      tmem_ld_wait();
-      if (n >= a.N) continue;
-      const int cg0 = tile * BN + ch * 16;
+    const int chunks = BN / 16;
+    int64_t local_tile = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local_tile) {
+      const int buf = (int)(local_tile & 1);
+      const uint32_t ph = (uint32_t)(local_tile >> 1) & 1;
+      const int ctile = (int)(tile % n_ctiles);
+      const int64_t n = (tile / n_ctiles) * BM + quarter * 32 + lane;  // output row of this thread
+      mbar_wait(acc_full(buf), ph);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t)(buf * P.tmem_cols) + ((uint32_t)(quarter * 32) << 16);
+      for (int ch = 0; ch < chunks; ++ch) {
+        uint32_t r[16];
+        tmem_ld16(t_addr + (uint32_t)(ch * 16), r);
+        tmem_ld_wait();
+        if (n >= a.N) continue;
+        const int cg0 = ctile * BN + ch * 16;
 #pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        const int cg = cg0 + j;
-        if (cg >= a.Nc) break;
-        float v[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          v[e] = __uint_as_float(r[j + e]);
-          if (a.bias && cg + e < a.Nc) v[e] += __ldg(a.bias + cg + e);
-          if (a.act == 1) v[e] = fmaxf(v[e], 0.f);
-        }
-        if (vec_store && cg + 3 < a.Nc) {
-          const int cp = cg / a.Cw, cc = cg - cp * a.Cw;
-          *reinterpret_cast<float4*>(a.C + cp * a.sCp + n * a.ldc + cc) = make_float4(v[0], v[1], v[2], v[3]);
-        } else {
+        for (int j = 0; j < 16; j += 4) {
+          const int cg = cg0 + j;
+          if (cg >= a.Nc) break;
+          float v[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            if (cg + e >= a.Nc) break;
-            const int cp = (cg + e) / a.Cw, cc = (cg + e) - cp * a.Cw;
-            a.C[cp * a.sCp + n * a.ldc + cc] = v[e];
+            v[e] = __uint_as_float(r[j + e]);
+            if (a.bias && cg + e < a.Nc) v[e] += __ldg(a.bias + cg + e);
+            if (a.act == 1) v[e] = fmaxf(v[e], 0.f);
+          }
+          if (vec_store && cg + 3 < a.Nc) {
+            const int cp = cg / a.Cw, cc = cg - cp * a.Cw;
+            *reinterpret_cast<float4*>(a.C + cp * a.sCp + n * a.ldc + cc) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (cg + e >= a.Nc) break;
+              const int cp = (cg + e) / a.Cw, cc = (cg + e) - cp * a.Cw;
+              a.C[cp * a.sCp + n * a.ldc + cc] = v[e];
+            }
           }
         }
       }
-    }
-  } else if (lane == 0) {
-    // ================= TMA + MMA issuer (one thread) =================
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-    const uint8_t* bsrc = P.bprep + (int64_t)tile * total_kb * 2 * b_img;
-    for (int kbi = 0; kbi < total_kb; ++kbi) {
-      const int s = kbi & 1;
-      if (kbi >= STAGES) mbar_wait(empty(s), ((kbi >> 1) - 1) & 1);
-      const uint32_t st_base = smem_base + s * stage_bytes;
-      mbar_expect_tx(b_full(s), 2u * b_img);
-      bulk_copy_g2s(st_base + 2u * A_TILE, bsrc + (int64_t)kbi * 2 * b_img, 2u * b_img, b_full(s));
-      mbar_wait(a_full(s), (kbi >> 1) & 1);
-      mbar_wait(b_full(s), (kbi >> 1) & 1);
-      tc_fence_after();
-      const int kb = kbi % P.nkb;
-      const int ksteps = (kb == P.nkb - 1) ? last_ksteps : BKB / 16;
-      const uint64_t dAh = make_desc(st_base), dAl = make_desc(st_base + A_TILE);
-      const uint64_t dBh = make_desc(st_base + 2u * A_TILE), dBl = make_desc(st_base + 2u * A_TILE + b_img);
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const uint64_t adv = (uint64_t)(ks * 2);  // 32 bytes per K-step, in 16-byte units
-        umma_bf16(tmem_base, dAh + adv, dBh + adv, idesc, (kbi | ks) != 0);
-        umma_bf16(tmem_base, dAh + adv, dBl + adv, idesc, 1u);
-        umma_bf16(tmem_base, dAl + adv, dBh + adv, idesc, 1u);
-      }
-      umma_commit(empty(s));  // arrives when every MMA issued so far has completed
+      tc_fence_before();
+      mbar_arrive(acc_empty(buf));
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+  if (warp == WARP_MMA) tmem_dealloc(tmem_base, (uint32_t)(2 * P.tmem_cols));
 }
 
-static size_t smem_bytes_for(int BN) { return (size_t)STAGES * (2 * A_TILE + 2 * BN * 128) + 1024 + 64; }
+// ---------------------------------------------------------------------------------------------
+// TMA-fed variant (the production path when the A planes are 16-byte aligned with regular strides).
+//
+// The fp32 A block [128 rows x 64 reduction elements] is no longer pulled through registers / L1 by
+// the converters: one producer lane issues a tensor-map TMA load (cp.async.bulk.tensor, zero-filled
+// out of bounds) that lands the raw block in the stage buffer, S stages (up to 128 KB per SM) ahead
+// of the arithmetic.  The converters read the raw block from shared memory, synchronise among
+// themselves, and overwrite the same 32 KB in place with the bf16 hi / lo UMMA images (a raw fp32
+// block and its two bf16 images have the same size).  The epilogue transposes each 32 x 64
+// accumulator chunk through shared memory so that global stores are full 256-byte row segments.
+//
+//   warps 0-7 converters | warp 8 producer (TMA A + bulk B) | warp 9 MMA issuer | warps 10-13 epilogue
+// ---------------------------------------------------------------------------------------------
+struct TmaArgs {
+  TcArgs tc;
+  int32_t rank;  // 2: rows = flat (b, v) index; 3: (k, v, b) coordinates
+  CUtensorMap amap[DSW_MAX_K];
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"(map), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+
+constexpr int EPI_PITCH = 64;                          // floats per staged row; 16-byte chunks XOR-swizzled by the row
+constexpr int EPI_BYTES = 32 * EPI_PITCH * 4;          // one warp's 32 x 64 staging chunk
+__device__ __forceinline__ int epi_off(int row, int chunk) { return row * EPI_PITCH + ((chunk ^ (row & 15)) << 2); }
+
+__global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_constant__ TmaArgs Q) {
+  extern __shared__ uint8_t smem_raw[];
+  const TcArgs& P = Q.tc;
+  const MixArgs& a = P.m;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int BN = P.BN;
+  const int S = P.stages;
+  const uint32_t b_img = (uint32_t)BN * 128u;
+  const uint32_t stage_bytes = 2u * A_TILE + 2u * b_img;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint8_t* epi_gen = smem_gen + (size_t)S * stage_bytes;
+  const uint32_t bars = smem_base + (uint32_t)S * stage_bytes + 4u * EPI_BYTES;
+  // barrier slots (8 bytes each): raw_full[S], a_full[S], b_full[S], empty[S], acc_full[2], acc_empty[2]; TMEM slot
+  auto raw_full = [&](int s) { return bars + 8u * s; };
+  auto a_full = [&](int s) { return bars + 8u * (S + s); };
+  auto b_full = [&](int s) { return bars + 8u * (2 * S + s); };
+  auto empty = [&](int s) { return bars + 8u * (3 * S + s); };
+  auto acc_full = [&](int b) { return bars + 8u * (4 * S + b); };
+  auto acc_empty = [&](int b) { return bars + 8u * (4 * S + 2 + b); };
+  const uint32_t tmem_slot = bars + 8u * (4 * S + 4);
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + (size_t)S * stage_bytes + 4 * EPI_BYTES + 8 * (4 * S + 4));
+
+  if (t == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(raw_full(s), 1);
+      mbar_init(a_full(s), N_CONV_WARPS * 32);
+      mbar_init(b_full(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == WARP_MMA) tmem_alloc(tmem_slot, (uint32_t)(2 * P.tmem_cols));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int total_kb = a.P * P.nkb;
+  const int last_ksteps = (a.Ka - (P.nkb - 1) * BKB + 15) / 16;  // K-steps (of 16) in a plane's last block
+  const int n_ctiles = P.n_ctiles;
+  const int64_t n_rtiles = (a.N + BM - 1) / BM;
+  const int64_t n_tiles = n_rtiles * n_ctiles;
+  const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const int64_t n_iters = my_tiles * total_kb;
+
+  if (warp < N_CONV_WARPS) {
+    // ================= converters: raw fp32 block (shared) -> bf16 hi / lo images, in place =================
+    const int q = t & 15;
+    for (int64_t it = 0; it < n_iters; ++it) {
+      const int s = (int)(it % S);
+      const uint32_t ph = (uint32_t)(it / S) & 1;
+      uint8_t* Ahi = smem_gen + (size_t)s * stage_bytes;
+      uint8_t* Alo = Ahi + A_TILE;
+      mbar_wait(raw_full(s), ph);
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(Ahi + ((t >> 4) + 16 * i) * 256 + q * 16);
+      asm volatile("bar.sync 1, %0;" ::"n"(N_CONV_WARPS * 32) : "memory");  // every converter has read its share
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t row = (t >> 4) + 16 * i;
+        __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+        split_bf16(v[i].x, h0, l0);
+        split_bf16(v[i].y, h1, l1);
+        split_bf16(v[i].z, h2, l2);
+        split_bf16(v[i].w, h3, l3);
+        const uint32_t off = swz(row, q >> 1) + (q & 1) * 8;
+        *reinterpret_cast<uint2*>(Ahi + off) = make_uint2(pack2(h0, h1), pack2(h2, h3));
+        *reinterpret_cast<uint2*>(Alo + off) = make_uint2(pack2(l0, l1), pack2(l2, l3));
+      }
+      fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
+      mbar_arrive(a_full(s));
+    }
+  } else if (warp == WARP_BLOAD) {
+    // ================= producer (one thread): TMA of the raw A block + bulk copy of the B images =================
+    if (lane == 0) {
+      int64_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int ctile = (int)(tile % n_ctiles);
+        const int64_t n0 = (tile / n_ctiles) * BM;
+        const uint8_t* bsrc = P.bprep + (int64_t)ctile * total_kb * 2 * b_img;
+        for (int kbi = 0; kbi < total_kb; ++kbi, ++it) {
+          const int s = (int)(it % S);
+          const uint32_t use = (uint32_t)(it / S);
+          if (use > 0) mbar_wait(empty(s), (use - 1) & 1);
+          const int p = kbi / P.nkb, kb = kbi - p * P.nkb;
+          const uint32_t st_base = smem_base + s * stage_bytes;
+          mbar_expect_tx(raw_full(s), 2u * A_TILE);
+          if (Q.rank == 2) {
+            tma_load_2d(st_base, &Q.amap[p], kb * BKB, (int)n0, raw_full(s));
+          } else {
+            const int bb = (int)(n0 / a.rows_per_batch);
+            tma_load_3d(st_base, &Q.amap[p], kb * BKB, (int)(n0 - (int64_t)bb * a.rows_per_batch), bb, raw_full(s));
+          }
+          mbar_expect_tx(b_full(s), 2u * b_img);
+          bulk_copy_g2s(st_base + 2u * A_TILE, bsrc + (int64_t)kbi * 2 * b_img, 2u * b_img, b_full(s));
+        }
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int64_t it = 0;
+      for (int64_t lt = 0; lt < my_tiles; ++lt) {
+        const int buf = (int)(lt & 1);
+        const uint32_t buse = (uint32_t)(lt >> 1);
+        if (buse > 0) {
+          mbar_wait(acc_empty(buf), (buse - 1) & 1);
+          tc_fence_after();
+        }
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * P.tmem_cols);
+        for (int kbi = 0; kbi < total_kb; ++kbi, ++it) {
+          const int s = (int)(it % S);
+          const uint32_t ph = (uint32_t)(it / S) & 1;
+          mbar_wait(a_full(s), ph);
+          mbar_wait(b_full(s), ph);
+          tc_fence_after();
+          const uint32_t st_base = smem_base + s * stage_bytes;
+          const int kb = kbi % P.nkb;
+          const int ksteps = (kb == P.nkb - 1) ? last_ksteps : BKB / 16;
+          const uint64_t dAh = make_desc(st_base), dAl = make_desc(st_base + A_TILE);
+          const uint64_t dBh = make_desc(st_base + 2u * A_TILE), dBl = make_desc(st_base + 2u * A_TILE + b_img);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint64_t adv = (uint64_t)(ks * 2);  // 32 bytes per K-step, in 16-byte units
+            umma_bf16(d_tmem, dAh + adv, dBh + adv, idesc, (kbi | ks) != 0);
+            umma_bf16(d_tmem, dAh + adv, dBl + adv, idesc, 1u);
+            umma_bf16(d_tmem, dAl + adv, dBh + adv, idesc, 1u);
+          }
+          umma_commit(empty(s));  // arrives when every MMA issued so far has completed
+        }
+        umma_commit(acc_full(buf));
+      }
+    }
+  } else {
+    // ================= epilogue (4 warps = the 4 TMEM lane quarters) =================
+    const int quarter = warp & 3;  // tcgen05.ld: a warp reads lanes 32*(warp%4) .. +31
+    float* stg = reinterpret_cast<float*>(epi_gen + (size_t)quarter * EPI_BYTES);
+    const bool vec_ok = (a.Cw % 4 == 0) && (a.ldc % 4 == 0) && (a.sCp % 4 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0);
+    const int half = lane >> 4, c4 = lane & 15;  // store phase: two rows per instruction, 16 lanes x float4 per row
+    for (int64_t lt = 0; lt < my_tiles; ++lt) {
+      const int64_t tile = blockIdx.x + lt * gridDim.x;
+      const int buf = (int)(lt & 1);
+      const uint32_t ph = (uint32_t)(lt >> 1) & 1;
+      const int ctile = (int)(tile % n_ctiles);
+      const int64_t row0 = (tile / n_ctiles) * BM + quarter * 32;  // first output row of this warp
+      mbar_wait(acc_full(buf), ph);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (uint32_t)(buf * P.tmem_cols) + ((uint32_t)(quarter * 32) << 16);
+      for (int cg = 0; cg < BN; cg += 64) {
+        const int ncol = min(64, BN - cg);  // multiple of 16
+        for (int cc = 0; cc < ncol; cc += 16) {
+          uint32_t r[16];
+          tmem_ld16(t_addr + (uint32_t)(cg + cc), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<uint4*>(stg + epi_off(lane, (cc + j) >> 2)) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        }
+        __syncwarp();
+        // columns of this lane in the store phase
+        const int col = ctile * BN + cg + c4 * 4;
+        const bool col_ok = (c4 * 4 < ncol) && (col < a.Nc);
+        if (col_ok) {
+          float bv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (a.bias && col + e < a.Nc) bv[e] = __ldg(a.bias + col + e);
+          const int cp = col / a.Cw, ccol = col - cp * a.Cw;
+          const bool vec = vec_ok && (col + 3 < a.Nc) && (ccol + 3 < a.Cw);
+          float* cbase = a.C + (int64_t)cp * a.sCp + ccol;
+#pragma unroll 4
+          for (int rr = 0; rr < 32; rr += 2) {
+            const int r_loc = rr + half;
+            const int64_t n = row0 + r_loc;
+            if (n >= a.N) continue;
+            float4 v = *reinterpret_cast<const float4*>(stg + epi_off(r_loc, c4));
+            v.x += bv[0], v.y += bv[1], v.z += bv[2], v.w += bv[3];
+            if (a.act == 1) v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+            if (vec) {
+              *reinterpret_cast<float4*>(cbase + n * a.ldc) = v;
+            } else {
+              const float ve[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (col + e >= a.Nc) break;
+                const int cpe = (col + e) / a.Cw, cce = (col + e) - cpe * a.Cw;
+                a.C[(int64_t)cpe * a.sCp + n * a.ldc + cce] = ve[e];
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive(acc_empty(buf));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WARP_MMA) tmem_dealloc(tmem_base, (uint32_t)(2 * P.tmem_cols));
+}
+
+static int tma_stages_for(int BN) {
+  const size_t stage = 2 * (size_t)A_TILE + 2 * (size_t)BN * 128;
+  const size_t avail = 226 * 1024 - 4 * (size_t)EPI_BYTES - 1024 - 512;
+  int s = (int)(avail / stage);
+  return std::max(1, std::min(s, 6));
+}
+static size_t tma_smem_bytes_for(int BN) {
+  return (size_t)tma_stages_for(BN) * (2 * A_TILE + 2 * BN * 128) + 4 * (size_t)EPI_BYTES + 1024 + 512;
+}
+
+static int stages_for(int BN) {
+  const size_t stage = 2 * (size_t)A_TILE + 2 * (size_t)BN * 128;
+  int s = (int)((220 * 1024) / stage);
+  const int cap = (int)g_options[DSW_OPT_RESERVED2].load() > 0 ? (int)g_options[DSW_OPT_RESERVED2].load() : 6;
+  return std::max(2, std::min(s, cap));
+}
+static size_t smem_bytes_for(int BN) { return (size_t)stages_for(BN) * (2 * A_TILE + 2 * BN * 128) + 1024 + 256; }
+
+// ---- host: tensor maps of the A planes (driver entry point fetched through the runtime) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess) {
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// Box = [64 reduction elements x 128 rows] of fp32, no swizzle, zero fill out of bounds.
+// rank 2 when the batch is contiguous (row n = flat index), rank 3 (k, v, b) when every 128-row tile
+// stays inside one sample.  Returns false when neither applies (caller uses the register-path kernel).
+static bool encode_a_maps(const MixArgs& a, TmaArgs* Q) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc || a.N >= ((int64_t)1 << 31)) return false;
+  const int64_t V = a.rows_per_batch;
+  const int64_t B = (a.N + V - 1) / V;
+  bool flat = true;
+  for (int p = 0; p < a.P; ++p) flat = flat && (a.a_sB[p] == V * a.a_sV[p] || B == 1);
+  if (!flat && (V % BM != 0)) return false;
+  Q->rank = flat ? 2 : 3;
+  for (int p = 0; p < a.P; ++p) {
+    if (a.a_sV[p] < a.Ka) return false;
+    cuuint64_t dims[3], strides[2];
+    cuuint32_t box[3] = {(cuuint32_t)BKB, (cuuint32_t)BM, 1}, estr[3] = {1, 1, 1};
+    if (flat) {
+      dims[0] = (cuuint64_t)a.Ka, dims[1] = (cuuint64_t)a.N;
+      strides[0] = (cuuint64_t)a.a_sV[p] * 4;
+    } else {
+      dims[0] = (cuuint64_t)a.Ka, dims[1] = (cuuint64_t)V, dims[2] = (cuuint64_t)B;
+      strides[0] = (cuuint64_t)a.a_sV[p] * 4, strides[1] = (cuuint64_t)a.a_sB[p] * 4;
+    }
+    const CUresult rc = enc(&Q->amap[p], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, flat ? 2 : 3, const_cast<float*>(a.A[p]), dims,
+                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) return false;
+  }
+  return true;
+}
 
 }  // namespace tc
 
@@ -387,17 +797,42 @@ int launch_mix_tc_ws(const MixArgs& a, void* prep, size_t prep_bytes, bool do_pr
   bool vec4 = (a.Ka % 4 == 0);
   for (int p = 0; p < a.P && vec4; ++p)
     vec4 = ((reinterpret_cast<uintptr_t>(a.A[p]) & 15) == 0) && (a.a_sB[p] % 4 == 0) && (a.a_sV[p] % 4 == 0);
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    DSW_CUDA_TRY(cudaGetDevice(&dev));
+    DSW_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  P.n_ctiles = n_tiles;
+  const int64_t total_tiles = ceil_div64(a.N, tc::BM) * n_tiles;
+  dim3 grid((unsigned)std::min<int64_t>(total_tiles, n_sm));
+
+  // ---- TMA-fed kernel: needs a tensor map per A plane ----
+  if (vec4 && g_options[DSW_OPT_RESERVED3].load(std::memory_order_relaxed) == 0 && tc::tma_stages_for(P.BN) >= 2) {
+    tc::TmaArgs Q;
+    Q.tc = P;
+    Q.tc.stages = tc::tma_stages_for(P.BN);
+    if (tc::encode_a_maps(a, &Q)) {
+      const size_t smem = tc::tma_smem_bytes_for(P.BN);
+      static std::atomic<bool> attr_tma{false};
+      if (!attr_tma.exchange(true))
+        DSW_CUDA_TRY(cudaFuncSetAttribute(tc::mix_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      tc::mix_tma_kernel<<<grid, tc::THREADS2, smem, st>>>(Q);
+      return check_launch();
+    }
+  }
+
   const size_t smem = tc::smem_bytes_for(P.BN);
-  dim3 grid((unsigned)ceil_div64(a.N, tc::BM), n_tiles);
+  P.stages = tc::stages_for(P.BN);
   static std::atomic<bool> attr_set[2] = {{false}, {false}};
   if (vec4) {
     if (!attr_set[1].exchange(true))
       DSW_CUDA_TRY(cudaFuncSetAttribute(tc::mix_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    tc::mix_tc_kernel<true><<<grid, tc::THREADS, smem, st>>>(P);
+    tc::mix_tc_kernel<true><<<grid, tc::THREADS2, smem, st>>>(P);
   } else {
     if (!attr_set[0].exchange(true))
       DSW_CUDA_TRY(cudaFuncSetAttribute(tc::mix_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    tc::mix_tc_kernel<false><<<grid, tc::THREADS, smem, st>>>(P);
+    tc::mix_tc_kernel<false><<<grid, tc::THREADS2, smem, st>>>(P);
   }
   return check_launch();
 }

@@ -50,6 +50,15 @@ def main():
             y = layer(x)
             y.backward(torch.ones_like(y))
         torch.cuda.synchronize()
+    elif what == "layer":  # one U-Net layer shape: profile_step.py layer n nside Fin Fout
+        nside, Fin, Fout = int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
+        lap = G.healpix_laplacian(nside)
+        layer = L.ConvCheb(Fin, Fout, 4, lap).to(dev)
+        x = torch.randn(32, lap.shape[0], Fin, device=dev, requires_grad=True)
+        for _ in range(n):
+            y = layer(x)
+            y.backward(torch.ones_like(y))
+        torch.cuda.synchronize()
     print("done", what, n)
 
 
