@@ -37,6 +37,12 @@ struct dsw_rb {
   int32_t* tile_ptr = nullptr;   // [n_tiles + 1] offsets into tile_row
   int32_t* tile_row = nullptr;   // source row ids, ascending inside a tile
   uint16_t* lidx = nullptr;      // [total_union] local index of ucol[e] inside its tile's list
+  // TMA pieces of a tile: runs of consecutive source rows cut into power-of-two lengths (one
+  // cp.async.bulk.tensor box each).  meta = (first local row << 8) | log2(length).
+  int32_t tile_pieces_max = 0;
+  int32_t* tpc_ptr = nullptr;    // [n_tiles + 1]
+  int32_t* tpc_row = nullptr;    // first source row of the piece
+  uint32_t* tpc_meta = nullptr;
   // Entry-major padded panels of a tile: entry u of row-block slot s at [tp_ptr[t] + u][s]; every
   // row-block of the tile is padded to the tile's longest union with zero weights / offset 0, so the
   // 32 slots of one entry step are contiguous (conflict-free broadcast reads, uniform trip counts).
@@ -120,6 +126,7 @@ struct MixArgs {
   const float* Bm = nullptr;
   int64_t sBp = 0, sBk = 0, sBc0 = 1, sBc1 = 0;
   const float* bias = nullptr;
+  int32_t bias_n = 0;   // bias is added to output columns c < bias_n (c indexes bias)
   float* C = nullptr;
   int64_t sCp = 0, ldc = 0;
   int32_t Cw = 0;   // width of one output plane
@@ -135,15 +142,19 @@ struct WgradArgs {
   int64_t t_sB[DSW_MAX_K];
   int64_t t_sV[DSW_MAX_K];
   int32_t K = 0, Fin = 0, Fout = 0;
+  // Ka planes on the Fin side (T[0..Ka)) x Kb planes on the Fout side (Y[0..Kb)), one of them 1:
+  //   Ka = K, Kb = 1:  dW[f][k][o] = sum_n T_k[n][f] dY[n][o]            (terms of x)
+  //   Ka = 1, Kb = K:  dW[f][k][o] = sum_n x[n][f] (T_k(L^T) dY)[n][o]   (terms of dY, the adjoint form)
+  int32_t Ka = 0, Kb = 1;
   int32_t rows_per_batch = 0;
   int64_t N = 0;
-  const float* dY = nullptr;  // [N][Fout]
+  const float* Y[DSW_MAX_K];  // [N][Fout] contiguous planes; Y[0] is dY itself (feeds dbias)
   float* dW = nullptr;        // [Fin][K][Fout]
   float* dbias = nullptr;     // [Fout] or null
   float* partial = nullptr;   // workspace [nsplit][K*Fin + 1][Fout]
   int32_t nsplit = 0;
 };
-int wgrad_pick_nsplit(int64_t N, int32_t K, int32_t Fin, int32_t Fout);
+int wgrad_pick_nsplit(int64_t N, int32_t Ka, int32_t Kb, int32_t Fin, int32_t Fout);
 int launch_wgrad_simt(const WgradArgs& a, cudaStream_t st);
 
 }  // namespace dsw

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) mix_simt_kernel(MixArgs a) {
   for (int j = 0; j < TN; ++j) {
     const int cg = c0 + tx * TN + j;
     if (cg >= a.Nc) continue;
-    const float bz = a.bias ? __ldg(a.bias + cg) : 0.f;
+    const float bz = (a.bias && cg < a.bias_n) ? __ldg(a.bias + cg) : 0.f;
     const int cp = cg / a.Cw, cc = cg - cp * a.Cw;
     float* __restrict__ Cb = a.C + cp * a.sCp + cc;
 #pragma unroll
@@ -145,10 +145,13 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradArgs a, int32_t ft
   __shared__ __align__(16) float Bs[WR][WT];
   const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
   const int mt = blockIdx.x;
-  const bool bias_tile = (mt == a.K * ftiles);
+  const bool bias_tile = (mt == a.Ka * ftiles);
   const int k = bias_tile ? 0 : mt / ftiles;
   const int f0 = bias_tile ? 0 : (mt - k * ftiles) * WT;
-  const int o0 = blockIdx.y * WT;
+  const int otiles = (a.Fout + WT - 1) / WT;
+  const int kb_plane = blockIdx.y / otiles;  // Fout-side plane
+  const int o0 = (blockIdx.y - kb_plane * otiles) * WT;
+  const float* __restrict__ Yp = a.Y[kb_plane];
   const int64_t r_begin = (int64_t)blockIdx.z * rows_per_split;
   const int64_t r_end = (r_begin + rows_per_split < a.N) ? r_begin + rows_per_split : a.N;
 
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradArgs a, int32_t ft
           va = (cc == 0) ? 1.f : 0.f;
         else if (f0 + cc < a.Fin)
           va = __ldg(Tk + row_offset(n, a.rows_per_batch, sB, sV) + f0 + cc);
-        if (o0 + cc < a.Fout) vb = __ldg(a.dY + n * a.Fout + o0 + cc);
+        if (o0 + cc < a.Fout) vb = __ldg(Yp + n * a.Fout + o0 + cc);
       }
       As[rr][cc] = va;
       Bs[rr][cc] = vb;
@@ -199,11 +202,11 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradArgs a, int32_t ft
     const int fl = ty * 4 + i;
     int64_t m;
     if (bias_tile) {
-      if (fl != 0) continue;
+      if (fl != 0 || kb_plane != 0) continue;
       m = prow - 1;
     } else {
       if (f0 + fl >= a.Fin) continue;
-      m = (int64_t)(f0 + fl) * a.K + k;  // reference weight layout [Fin][K][Fout]
+      m = (int64_t)(f0 + fl) * a.K + k + kb_plane;  // reference weight layout [Fin][K][Fout]
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -226,8 +229,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int32_t n
     dbias[i - n_w] = s;
 }
 
-int wgrad_pick_nsplit(int64_t N, int32_t K, int32_t Fin, int32_t Fout) {
-  const int64_t tiles = ((int64_t)K * ceil_div(Fin, WT) + 1) * ceil_div(Fout, WT);
+int wgrad_pick_nsplit(int64_t N, int32_t Ka, int32_t Kb, int32_t Fin, int32_t Fout) {
+  const int64_t tiles = ((int64_t)Ka * ceil_div(Fin, WT) + 1) * Kb * ceil_div(Fout, WT);
   int64_t ns = ceil_div64(148 * 4, tiles);           // ~4 CTAs per SM
   ns = std::min<int64_t>(ns, ceil_div64(N, 4 * WR)); // at least 4 row steps per split
   return (int)std::max<int64_t>(1, std::min<int64_t>(ns, 1024));
@@ -246,7 +249,7 @@ int launch_wgrad_simt(const WgradArgs& a, cudaStream_t st) {
   const int ftiles = ceil_div(a.Fin, WT);
   int64_t rps = ceil_div64(a.N, a.nsplit);
   rps = ceil_div64(rps, WR) * WR;
-  dim3 grid(a.K * ftiles + 1, ceil_div(a.Fout, WT), a.nsplit);
+  dim3 grid(a.Ka * ftiles + 1, a.Kb * ceil_div(a.Fout, WT), a.nsplit);
   wgrad_simt_kernel<<<grid, 256, 0, st>>>(a, ftiles, rps);
   return check_launch();
 }

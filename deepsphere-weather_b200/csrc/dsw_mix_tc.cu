@@ -23,6 +23,7 @@
 #include <algorithm>
 
 #include "dsw_internal.cuh"
+#include "dsw_tmap.cuh"
 
 namespace dsw {
 namespace tc {
@@ -424,7 +425,7 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tc_kernel(const __grid_consta
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             v[e] = __uint_as_float(r[j + e]);
-            if (a.bias && cg + e < a.Nc) v[e] += __ldg(a.bias + cg + e);
+            if (a.bias && cg + e < a.bias_n) v[e] += __ldg(a.bias + cg + e);
             if (a.act == 1) v[e] = fmaxf(v[e], 0.f);
           }
           if (vec_store && cg + 3 < a.Nc) {
@@ -467,18 +468,6 @@ struct TmaArgs {
   int32_t rank;  // 2: rows = flat (b, v) index; 3: (k, v, b) coordinates
   CUtensorMap amap[DSW_MAX_K];
 };
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-               "l"(map), "r"(c0), "r"(c1), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-      : "memory");
-}
 
 constexpr int EPI_PITCH = 64;                          // floats per staged row; 16-byte chunks XOR-swizzled by the row
 constexpr int EPI_BYTES = 32 * EPI_PITCH * 4;          // one warp's 32 x 64 staging chunk
@@ -659,7 +648,7 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
           float bv[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int e = 0; e < 4; ++e)
-            if (a.bias && col + e < a.Nc) bv[e] = __ldg(a.bias + col + e);
+            if (a.bias && col + e < a.bias_n) bv[e] = __ldg(a.bias + col + e);
           const int cp = col / a.Cw, ccol = col - cp * a.Cw;
           const bool vec = vec_ok && (col + 3 < a.Nc) && (ccol + 3 < a.Cw);
           float* cbase = a.C + (int64_t)cp * a.sCp + ccol;
@@ -708,35 +697,15 @@ static size_t tma_smem_bytes_for(int BN) {
 static int stages_for(int BN) {
   const size_t stage = 2 * (size_t)A_TILE + 2 * (size_t)BN * 128;
   int s = (int)((220 * 1024) / stage);
-  const int cap = (int)g_options[DSW_OPT_RESERVED2].load() > 0 ? (int)g_options[DSW_OPT_RESERVED2].load() : 6;
-  return std::max(2, std::min(s, cap));
+  return std::max(2, std::min(s, 6));
 }
 static size_t smem_bytes_for(int BN) { return (size_t)stages_for(BN) * (2 * A_TILE + 2 * BN * 128) + 1024 + 256; }
-
-// ---- host: tensor maps of the A planes (driver entry point fetched through the runtime) ----
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = []() -> EncodeTiledFn {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess) {
-      (void)cudaGetLastError();
-      return nullptr;
-    }
-    return reinterpret_cast<EncodeTiledFn>(p);
-  }();
-  return fn;
-}
 
 // Box = [64 reduction elements x 128 rows] of fp32, no swizzle, zero fill out of bounds.
 // rank 2 when the batch is contiguous (row n = flat index), rank 3 (k, v, b) when every 128-row tile
 // stays inside one sample.  Returns false when neither applies (caller uses the register-path kernel).
 static bool encode_a_maps(const MixArgs& a, TmaArgs* Q) {
-  EncodeTiledFn enc = encode_tiled_fn();
-  if (!enc || a.N >= ((int64_t)1 << 31)) return false;
+  if (a.N >= ((int64_t)1 << 31)) return false;
   const int64_t V = a.rows_per_batch;
   const int64_t B = (a.N + V - 1) / V;
   bool flat = true;
@@ -745,19 +714,16 @@ static bool encode_a_maps(const MixArgs& a, TmaArgs* Q) {
   Q->rank = flat ? 2 : 3;
   for (int p = 0; p < a.P; ++p) {
     if (a.a_sV[p] < a.Ka) return false;
-    cuuint64_t dims[3], strides[2];
-    cuuint32_t box[3] = {(cuuint32_t)BKB, (cuuint32_t)BM, 1}, estr[3] = {1, 1, 1};
+    uint64_t dims[3], strides[2];
+    const uint32_t box[3] = {(uint32_t)BKB, (uint32_t)BM, 1};
     if (flat) {
-      dims[0] = (cuuint64_t)a.Ka, dims[1] = (cuuint64_t)a.N;
-      strides[0] = (cuuint64_t)a.a_sV[p] * 4;
+      dims[0] = (uint64_t)a.Ka, dims[1] = (uint64_t)a.N;
+      strides[0] = (uint64_t)a.a_sV[p] * 4;
     } else {
-      dims[0] = (cuuint64_t)a.Ka, dims[1] = (cuuint64_t)V, dims[2] = (cuuint64_t)B;
-      strides[0] = (cuuint64_t)a.a_sV[p] * 4, strides[1] = (cuuint64_t)a.a_sB[p] * 4;
+      dims[0] = (uint64_t)a.Ka, dims[1] = (uint64_t)V, dims[2] = (uint64_t)B;
+      strides[0] = (uint64_t)a.a_sV[p] * 4, strides[1] = (uint64_t)a.a_sB[p] * 4;
     }
-    const CUresult rc = enc(&Q->amap[p], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, flat ? 2 : 3, const_cast<float*>(a.A[p]), dims,
-                            strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS) return false;
+    if (!encode_f32_map(&Q->amap[p], a.A[p], flat ? 2 : 3, dims, strides, box)) return false;
   }
   return true;
 }
@@ -808,7 +774,7 @@ int launch_mix_tc_ws(const MixArgs& a, void* prep, size_t prep_bytes, bool do_pr
   dim3 grid((unsigned)std::min<int64_t>(total_tiles, n_sm));
 
   // ---- TMA-fed kernel: needs a tensor map per A plane ----
-  if (vec4 && g_options[DSW_OPT_RESERVED3].load(std::memory_order_relaxed) == 0 && tc::tma_stages_for(P.BN) >= 2) {
+  if (vec4 && g_options[DSW_OPT_NO_TMA].load(std::memory_order_relaxed) == 0 && tc::tma_stages_for(P.BN) >= 2) {
     tc::TmaArgs Q;
     Q.tc = P;
     Q.tc.stages = tc::tma_stages_for(P.BN);

@@ -77,6 +77,9 @@ struct HostRb {
   int32_t n_tiles = 0, tile_rows_max = 0;
   std::vector<int32_t> tile_ptr, tile_row;
   std::vector<uint16_t> lidx;
+  int32_t tile_pieces_max = 0;
+  std::vector<int32_t> tpc_ptr, tpc_row;
+  std::vector<uint32_t> tpc_meta;
   int32_t tile_len_max = 0;
   std::vector<int32_t> tp_ptr;
   std::vector<float> tp_val;      // 4 floats per (step, slot)
@@ -105,6 +108,28 @@ static void build_tiles(HostRb& rb) {
   if (!fits16) {  // tile layout unusable; kernels fall back
     rb.n_tiles = 0, rb.tile_rows_max = 0;
     return;
+  }
+  // TMA pieces: runs of consecutive source rows, cut into power-of-two boxes (<= 128 rows)
+  rb.tpc_ptr.assign(static_cast<size_t>(rb.n_tiles) + 1, 0);
+  for (int32_t t = 0; t < rb.n_tiles; ++t) {
+    const int32_t r0 = rb.tile_ptr[t], r1 = rb.tile_ptr[t + 1];
+    int32_t i = r0;
+    while (i < r1) {
+      int32_t j = i + 1;
+      while (j < r1 && rb.tile_row[j] == rb.tile_row[j - 1] + 1) ++j;
+      int32_t len = j - i, at = i;
+      while (len > 0) {
+        int32_t lg = 0;
+        while ((2 << lg) <= len && lg < 7) ++lg;
+        rb.tpc_row.push_back(rb.tile_row[at]);
+        rb.tpc_meta.push_back((static_cast<uint32_t>(at - r0) << 8) | static_cast<uint32_t>(lg));
+        at += 1 << lg;
+        len -= 1 << lg;
+      }
+      i = j;
+    }
+    rb.tpc_ptr[t + 1] = static_cast<int32_t>(rb.tpc_row.size());
+    rb.tile_pieces_max = std::max(rb.tile_pieces_max, rb.tpc_ptr[t + 1] - rb.tpc_ptr[t]);
   }
   // entry-major padded panels
   rb.tp_ptr.assign(static_cast<size_t>(rb.n_tiles) + 1, 0);
@@ -217,6 +242,10 @@ static cudaError_t upload_rb(dsw_rb* d, const HostRb& h, cudaStream_t st) {
     if ((e = upload(&d->tile_ptr, h.tile_ptr, st)) != cudaSuccess) return e;
     if ((e = upload(&d->tile_row, h.tile_row, st)) != cudaSuccess) return e;
     if ((e = upload(&d->lidx, h.lidx, st)) != cudaSuccess) return e;
+    d->tile_pieces_max = h.tile_pieces_max;
+    if ((e = upload(&d->tpc_ptr, h.tpc_ptr, st)) != cudaSuccess) return e;
+    if ((e = upload(&d->tpc_row, h.tpc_row, st)) != cudaSuccess) return e;
+    if ((e = upload(&d->tpc_meta, h.tpc_meta, st)) != cudaSuccess) return e;
     d->tile_len_max = h.tile_len_max;
     if ((e = upload(&d->tp_ptr, h.tp_ptr, st)) != cudaSuccess) return e;
     float* tv = nullptr;
@@ -240,6 +269,9 @@ static void free_rb(dsw_rb* r) {
   cudaFree(r->tile_ptr);
   cudaFree(r->tile_row);
   cudaFree(r->lidx);
+  cudaFree(r->tpc_ptr);
+  cudaFree(r->tpc_row);
+  cudaFree(r->tpc_meta);
   cudaFree(r->tp_ptr);
   cudaFree(r->tp_val);
   cudaFree(r->tp_off);

@@ -11,6 +11,7 @@
 //  * hop_csr_kernel — plain CSR, float4 or scalar lanes; used for F % 4 != 0, unaligned strides,
 //    and operators whose rows do not overlap (pool matrices).
 #include "dsw_internal.cuh"
+#include "dsw_tmap.cuh"
 
 namespace dsw {
 
@@ -313,12 +314,42 @@ struct TeamHopPlan {
   const uint32_t* tp_off;
   const int32_t* tile_ptr;
   const int32_t* tile_row;
+  const int32_t* tpc_ptr;
+  const int32_t* tpc_row;
+  const uint32_t* tpc_meta;
+  int32_t cap_pieces;
   int32_t n_blocks, n_rows, cap_len, cap_rows;
   int32_t n_slabs;        // ceil(F / 64)
   int32_t n_items;        // B * n_slabs
   int32_t items_per_cta;
   int32_t n_teams;
+  int32_t debug_skip;     // timing experiments only: 1 = skip staging, 2 = skip the entry loop
 };
+
+struct HopMaps {
+  CUtensorMap m[8];  // box rows 1, 2, 4, .. 128 over the gather source [B][n_cols][F]
+};
+
+__device__ __forceinline__ uint32_t hop_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void hop_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void hop_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void hop_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
 
 __device__ __forceinline__ void team_sync(int team) {
   asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(TEAM_THREADS) : "memory");
@@ -334,7 +365,9 @@ __device__ __forceinline__ void fma_step(float4 (&acc)[4][4], const float4& w, c
   }
 }
 
-__global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1) hop_team_kernel(const TeamHopPlan P, const HopArgs a) {
+template <bool TMA>
+__global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1)
+    hop_team_kernel(const TeamHopPlan P, const HopArgs a, const __grid_constant__ HopMaps maps) {
   extern __shared__ __align__(256) uint8_t tile_smem[];
   const int tid = threadIdx.x;
   const int tile = blockIdx.x;
@@ -350,6 +383,11 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1) hop_team_kernel(co
   float4* s_val = reinterpret_cast<float4*>(tile_smem + (size_t)P.n_teams * xbuf_bytes);
   uint32_t* s_off = reinterpret_cast<uint32_t*>(s_val + (size_t)cap_steps * DSW_TILE_BLOCKS);
   int32_t* s_row = reinterpret_cast<int32_t*>(s_off + (size_t)cap_steps * DSW_TILE_BLOCKS);
+  // TMA variant: s_row holds the pieces (first source row), s_meta their (local row, log2 length)
+  uint32_t* s_meta = reinterpret_cast<uint32_t*>(s_row + ((P.cap_rows + 1) & ~1));
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_meta + ((P.cap_pieces + 1) & ~1));
+  const int pc0 = TMA ? __ldg(P.tpc_ptr + tile) : 0;
+  const int npieces = TMA ? __ldg(P.tpc_ptr + tile + 1) - pc0 : 0;
 
   {
     const float4* gv = P.tp_val + (size_t)t0 * DSW_TILE_BLOCKS;
@@ -359,7 +397,16 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1) hop_team_kernel(co
       s_val[i] = i < n_real ? __ldg(gv + i) : make_float4(0.f, 0.f, 0.f, 0.f);
       s_off[i] = i < n_real ? __ldg(go + i) : 0u;
     }
-    for (int i = tid; i < nrows; i += blockDim.x) s_row[i] = __ldg(P.tile_row + r0 + i);
+    if (TMA) {
+      for (int i = tid; i < npieces; i += blockDim.x) {
+        s_row[i] = __ldg(P.tpc_row + pc0 + i);
+        s_meta[i] = __ldg(P.tpc_meta + pc0 + i);
+      }
+      if (tid < MAX_TEAMS) hop_mbar_init(hop_smem_u32(s_bar + tid), 1);
+      if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    } else {
+      for (int i = tid; i < nrows; i += blockDim.x) s_row[i] = __ldg(P.tile_row + r0 + i);
+    }
   }
   __syncthreads();
 
@@ -387,6 +434,7 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1) hop_team_kernel(co
   int ch[4];
   ch[0] = (int)(cA >> 2), ch[1] = (int)(cB >> 2), ch[2] = ch[0] + 32, ch[3] = ch[1] + 32;
 
+  uint32_t phase = 0;
   const int item_begin = blockIdx.y * P.items_per_cta;
   const int item_end = min(item_begin + P.items_per_cta, P.n_items);
   for (int item = item_begin + team; item < item_end; item += P.n_teams) {
@@ -394,7 +442,20 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1) hop_team_kernel(co
     const int slab_f = min(64, a.F - slab * 64);       // channels in this slab (multiple of 4)
     const int cpr = slab_f >> 2;                        // 16-byte chunks per row
     // ---- stage the tile's source rows for this item ----
-    {
+    if (TMA && P.debug_skip == 1) {
+    } else if (TMA) {
+      // one lane issues a tensor-map box per piece (run of consecutive source rows); the copies bypass
+      // registers and L1, complete on the team's mbarrier, and out-of-range channels are zero-filled
+      if (tt == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const uint32_t bar = hop_smem_u32(s_bar + team);
+        hop_mbar_expect_tx(bar, (uint32_t)nrows * 256u);
+        for (int i = 0; i < npieces; ++i) {
+          const uint32_t meta = s_meta[i];
+          tma_load_3d(xs_u32 + (meta >> 8) * 256u, &maps.m[meta & 7u], slab * 64, s_row[i], b, bar);
+        }
+      }
+    } else {
       const float* xb = a.X + (int64_t)b * a.x_sB + slab * 64;
       const int c = tt & 15;
       if (c < cpr) {
@@ -454,8 +515,14 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1) hop_team_kernel(co
                                     fmaf(g[r][j].z, inv_alpha, acc[r][j].z), fmaf(g[r][j].w, inv_alpha, acc[r][j].w));
       }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    team_sync(team);
+    if (TMA && P.debug_skip == 1) {
+    } else if (TMA) {
+      hop_mbar_wait(hop_smem_u32(s_bar + team), phase);
+      phase ^= 1u;
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      team_sync(team);
+    }
 
     {
       auto load_x = [&](uint32_t o, float4(&x)[4]) {
@@ -472,7 +539,7 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1) hop_team_kernel(co
       load_x(po[0], x0);
       o1 = po[DSW_TILE_BLOCKS];
 #pragma unroll 1
-      for (int u = 0; u < wlen; u += 2) {
+      for (int u = 0; u < (P.debug_skip == 2 ? 0 : wlen); u += 2) {
         w1 = pw[(u + 1) * DSW_TILE_BLOCKS];
         load_x(o1, x1);
         o2 = po[(u + 2) * DSW_TILE_BLOCKS];
@@ -522,18 +589,21 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
   // 32-bit byte offsets inside one sample: (n_cols - 1) * x_sV * 4 + F * 4 must fit
   const bool off32 = ((int64_t)A.n_cols * a.x_sV + a.F) * 4 < ((int64_t)1 << 32);
   if (v4 && rb.R == 4 && hop_mode == 0 && rb.n_tiles > 0) {
-    const size_t panels = (size_t)(rb.tile_len_max + PANEL_PAD) * DSW_TILE_BLOCKS * 20 + (size_t)rb.tile_rows_max * 4 + 64;
+    const size_t panels = (size_t)(rb.tile_len_max + PANEL_PAD) * DSW_TILE_BLOCKS * 20 + (size_t)((rb.tile_rows_max + 1) & ~1) * 4 +
+                          (size_t)((rb.tile_pieces_max + 1) & ~1) * 4 + 8 * MAX_TEAMS + 64;
     const size_t xbuf = (size_t)rb.tile_rows_max * 256;
     int n_teams = panels < 200 * 1024 ? (int)std::min<size_t>(MAX_TEAMS, (226 * 1024 - panels) / std::max<size_t>(xbuf, 1)) : 0;
     if (n_teams >= 1) {
       TeamHopPlan P{};
       P.blkptr = rb.blkptr, P.tp_ptr = rb.tp_ptr, P.tp_val = rb.tp_val, P.tp_off = rb.tp_off;
       P.tile_ptr = rb.tile_ptr, P.tile_row = rb.tile_row;
+      P.tpc_ptr = rb.tpc_ptr, P.tpc_row = rb.tpc_row, P.tpc_meta = rb.tpc_meta, P.cap_pieces = rb.tile_pieces_max;
       P.n_blocks = rb.n_blocks, P.n_rows = A.n_rows, P.cap_len = rb.tile_len_max, P.cap_rows = rb.tile_rows_max;
       P.n_slabs = ceil_div(a.F, 64);
       P.n_items = a.B * P.n_slabs;
       n_teams = std::min(n_teams, P.n_items);
       P.n_teams = n_teams;
+      P.debug_skip = (int)g_options[DSW_OPT_DEBUG].load(std::memory_order_relaxed);
       // items per CTA: a few per team to amortise the staged panels, while keeping >= ~3 waves of CTAs
       int ipc = n_teams;
       while (ipc < 4 * n_teams && ipc * 2 <= P.n_items && (int64_t)rb.n_tiles * ceil_div(P.n_items, ipc * 2) >= 148 * 3)
@@ -541,10 +611,28 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
       P.items_per_cta = ipc;
       const size_t smem = (size_t)n_teams * xbuf + panels;
       dim3 grid(rb.n_tiles, ceil_div(P.n_items, ipc));
-      static std::atomic<bool> attr_set{false};
-      if (!attr_set.exchange(true))
-        DSW_CUDA_TRY(cudaFuncSetAttribute(hop_team_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-      hop_team_kernel<<<grid, TEAM_THREADS * MAX_TEAMS, smem, st>>>(P, a);
+      // tensor maps of the gather source [B][n_cols][F] with boxes of 1 .. 128 rows x 64 channels
+      HopMaps maps;
+      bool tma = g_options[DSW_OPT_NO_TMA].load(std::memory_order_relaxed) == 0 && rb.tile_pieces_max > 0 &&
+                 rb.tile_pieces_max <= rb.tile_rows_max && a.x_sV >= a.F;
+      if (tma) {
+        const uint64_t dims[3] = {(uint64_t)a.F, (uint64_t)A.n_cols, (uint64_t)a.B};
+        const uint64_t strides[2] = {(uint64_t)a.x_sV * 4, (uint64_t)std::max<int64_t>(a.x_sB, 1) * 4};
+        for (int j = 0; j < 8 && tma; ++j) {
+          const uint32_t box[3] = {64u, 1u << j, 1u};
+          tma = (1 << j) > A.n_cols ? (maps.m[j] = maps.m[j - 1], true) : encode_f32_map(&maps.m[j], a.X, 3, dims, strides, box);
+        }
+      }
+      static std::atomic<bool> attr_set[2] = {{false}, {false}};
+      if (tma) {
+        if (!attr_set[1].exchange(true))
+          DSW_CUDA_TRY(cudaFuncSetAttribute(hop_team_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        hop_team_kernel<true><<<grid, TEAM_THREADS * MAX_TEAMS, smem, st>>>(P, a, maps);
+      } else {
+        if (!attr_set[0].exchange(true))
+          DSW_CUDA_TRY(cudaFuncSetAttribute(hop_team_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        hop_team_kernel<false><<<grid, TEAM_THREADS * MAX_TEAMS, smem, st>>>(P, a, maps);
+      }
       return check_launch();
     }
   }

@@ -116,6 +116,7 @@ struct WtcArgs {
   int32_t ftiles;      // ceil(Fin / 64)
   int32_t tmem_cols;
   int32_t kb_per_split;
+  int32_t otiles;      // column tiles per Fout-side plane
 };
 
 __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WtcArgs P) {
@@ -150,8 +151,10 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  const int mtile = blockIdx.x, ntile = blockIdx.y, split = blockIdx.z;
-  const int n_half = a.K * P.ftiles;
+  const int mtile = blockIdx.x, split = blockIdx.z;
+  const int kb_plane = blockIdx.y / P.otiles, ntile = blockIdx.y - kb_plane * P.otiles;  // Fout-side plane, column tile
+  const float* __restrict__ Yp = a.Y[kb_plane];
+  const int n_half = a.Ka * P.ftiles;
   const int64_t r_begin = (int64_t)split * P.kb_per_split * KB;
   const int64_t r_end = (r_begin + (int64_t)P.kb_per_split * KB < a.N) ? r_begin + (int64_t)P.kb_per_split * KB : a.N;
   const int nkb = (r_end > r_begin) ? (int)((r_end - r_begin + KB - 1) / KB) : 0;
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
         hsrc[h] = nullptr, h_sB[h] = 0, h_sV[h] = 0, h_valid_f[h] = 0;
       }
     }
-    const bool do_bias = (mtile == 0) && (a.dbias != nullptr);
+    const bool do_bias = (mtile == 0) && (kb_plane == 0) && (a.dbias != nullptr);
     float4 bsum[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) bsum[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
             const int o = o_base + (u - 2) * 64 + q * 4;
             const int avail = a.Fout - o;
             if (avail > 0) {
-              const float* src = a.dY + n * a.Fout + o;
+              const float* src = Yp + n * a.Fout + o;
               if (avail >= 4 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
                 v = __ldg(reinterpret_cast<const float4*>(src));
               } else {
@@ -312,7 +315,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
     int64_t m = -1;
     if (ht < n_half) {
       const int k = ht / P.ftiles, f0 = (ht - k * P.ftiles) * 64;
-      if (f0 + fl < a.Fin) m = (int64_t)(f0 + fl) * a.K + k;
+      if (f0 + fl < a.Fin) m = (int64_t)(f0 + fl) * a.K + k + kb_plane;
     }
     const int chunks = BN / 16;
     for (int ch = (chunks * part) / 4; ch < (chunks * (part + 1)) / 4; ++ch) {
@@ -362,12 +365,12 @@ static size_t smem_bytes_for(int nb) { return (size_t)STAGES * (2 * 2 * BLK + 2 
 
 }  // namespace wtc
 
-static void wgrad_tc_geometry(int64_t N, int32_t K, int32_t Fin, int32_t Fout, int& BN, int& ntiles, int& mtiles,
-                              int& nsplit, int& kb_per_split) {
+static void wgrad_tc_geometry(int64_t N, int32_t Ka, int32_t Kb, int32_t Fin, int32_t Fout, int& BN, int& ntiles,
+                              int& mtiles, int& nsplit, int& kb_per_split) {
   BN = std::min(256, (Fout + 15) / 16 * 16);
-  ntiles = (Fout + BN - 1) / BN;
+  ntiles = Kb * ((Fout + BN - 1) / BN);
   const int ftiles = (Fin + 63) / 64;
-  mtiles = (K * ftiles + 1) / 2;
+  mtiles = (Ka * ftiles + 1) / 2;
   const int64_t total_kb = (N + wtc::KB - 1) / wtc::KB;
   int64_t ns = std::max<int64_t>(1, 148 / ((int64_t)mtiles * ntiles));
   ns = std::min<int64_t>(ns, std::max<int64_t>(1, total_kb / 4));
@@ -375,25 +378,26 @@ static void wgrad_tc_geometry(int64_t N, int32_t K, int32_t Fin, int32_t Fout, i
   nsplit = (int)((total_kb + kb_per_split - 1) / kb_per_split);
 }
 
-int wgrad_tc_nsplit(int64_t N, int32_t K, int32_t Fin, int32_t Fout) {
+int wgrad_tc_nsplit(int64_t N, int32_t Ka, int32_t Kb, int32_t Fin, int32_t Fout) {
   int BN, ntiles, mtiles, nsplit, kbps;
-  wgrad_tc_geometry(N, K, Fin, Fout, BN, ntiles, mtiles, nsplit, kbps);
+  wgrad_tc_geometry(N, Ka, Kb, Fin, Fout, BN, ntiles, mtiles, nsplit, kbps);
   return nsplit;
 }
 
-size_t wgrad_tc_partial_bytes(int64_t N, int32_t K, int32_t Fin, int32_t Fout) {
-  return (size_t)wgrad_tc_nsplit(N, K, Fin, Fout) * ((size_t)K * Fin + 1) * Fout * sizeof(float);
+size_t wgrad_tc_partial_bytes(int64_t N, int32_t Ka, int32_t Kb, int32_t Fin, int32_t Fout) {
+  return (size_t)wgrad_tc_nsplit(N, Ka, Kb, Fin, Fout) * ((size_t)Ka * Kb * Fin + 1) * Fout * sizeof(float);
 }
 
 // Writes wgrad_tc_nsplit() partials at a.partial; the caller sums them with launch_wgrad_reduce.
 int launch_wgrad_tc(const WgradArgs& a, size_t partial_bytes, cudaStream_t st) {
   if (!a.partial) return DSW_ERR_UNSUPPORTED;
-  if (partial_bytes < wgrad_tc_partial_bytes(a.N, a.K, a.Fin, a.Fout)) return DSW_ERR_UNSUPPORTED;
+  if (partial_bytes < wgrad_tc_partial_bytes(a.N, a.Ka, a.Kb, a.Fin, a.Fout)) return DSW_ERR_UNSUPPORTED;
   if (a.N >= (int64_t)1 << 31) return DSW_ERR_UNSUPPORTED;
   wtc::WtcArgs P;
   P.w = a;
   int ntiles, mtiles, nsplit;
-  wgrad_tc_geometry(a.N, a.K, a.Fin, a.Fout, P.BN, ntiles, mtiles, nsplit, P.kb_per_split);
+  wgrad_tc_geometry(a.N, a.Ka, a.Kb, a.Fin, a.Fout, P.BN, ntiles, mtiles, nsplit, P.kb_per_split);
+  P.otiles = ntiles / a.Kb;
   P.w.nsplit = nsplit;
   P.nb = (P.BN + 63) / 64;
   P.ftiles = (a.Fin + 63) / 64;

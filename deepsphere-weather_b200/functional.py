@@ -157,8 +157,11 @@ class ChebConvFunction(torch.autograd.Function):
         _lib.check(rc, "dsw_cheb_fwd")
         # Only x and W are saved: callers modify our output in place (`x_out *= rezero_weight`,
         # my_models_graph.py:213), so the backward recomputes the Chebyshev terms instead.
-        keep = _SAVE_TERMS and K > 1 and lib.dsw_get_option(_OPT_L2_CHUNK) <= 1 and (
-            ctx.needs_input_grad[1] or (bias is not None and ctx.needs_input_grad[2]))
+        # The forward's terms of x are kept for the weight gradient only when both directions use the
+        # orders that produce / consume them (dsw_cheb.cu); otherwise dW comes from the terms of dy.
+        keep = (_SAVE_TERMS and K > 1 and lib.dsw_get_option(_OPT_L2_CHUNK) <= 1
+                and lib.dsw_cheb_fwd_algo(Fin, Fout, K) == 1 and lib.dsw_cheb_bwd_algo(Fin, Fout, K) == 2
+                and (ctx.needs_input_grad[1] or (bias is not None and ctx.needs_input_grad[2])))
         ctx.save_for_backward(x, w, *([ws] if keep else []))
         ctx.plan = plan
         ctx.has_bias = bias is not None
@@ -174,27 +177,23 @@ class ChebConvFunction(torch.autograd.Function):
         B, V, Fin = x.shape
         _, K, Fout = w.shape
         dy = dy.contiguous()
-        dx = dw = db = None
-        st = _stream_ptr(x.device)
+        need_dx = ctx.needs_input_grad[0]
+        need_dw = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+        if not (need_dx or need_dw):
+            return None, None, None, None
+        dx = torch.empty((B, V, Fin), dtype=torch.float32, device=x.device) if need_dx else None
+        dw = torch.empty_like(w) if need_dw else None
+        db = torch.empty(Fout, dtype=torch.float32, device=x.device) if (need_dw and ctx.has_bias) else None
+        have_saved = 1 if (terms_ptr is not None or not need_dw) else 0
         with torch.cuda.device(x.device):
-            if ctx.needs_input_grad[0]:
-                dx = torch.empty((B, V, Fin), dtype=torch.float32, device=x.device)
-                ws = _workspace(lib.dsw_cheb_bwd_data_workspace_bytes(B, V, Fin, Fout, K), x.device)
-                rc = lib.dsw_cheb_bwd_data(
-                    plan.handle, dy.data_ptr(), w.data_ptr(), dx.data_ptr(), B, Fin, Fout, K,
-                    ws.data_ptr(), ws.numel(), st,
-                )
-                _lib.check(rc, "dsw_cheb_bwd_data")
-            if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-                dw = torch.empty_like(w)
-                db = torch.empty(Fout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
-                ws = _workspace(lib.dsw_cheb_bwd_weight_workspace_bytes(B, V, Fin, Fout, K), x.device)
-                rc = lib.dsw_cheb_bwd_weight(
-                    plan.handle, x.data_ptr(), x.stride(0), x.stride(1), dy.data_ptr(), terms_ptr, dw.data_ptr(),
-                    db.data_ptr() if db is not None else None, B, Fin, Fout, K,
-                    ws.data_ptr(), ws.numel(), st,
-                )
-                _lib.check(rc, "dsw_cheb_bwd_weight")
+            ws = _workspace(lib.dsw_cheb_bwd_workspace_bytes(B, V, Fin, Fout, K, have_saved), x.device)
+            rc = lib.dsw_cheb_bwd(
+                plan.handle, x.data_ptr(), x.stride(0), x.stride(1), dy.data_ptr(), w.data_ptr(), terms_ptr,
+                dx.data_ptr() if dx is not None else None, dw.data_ptr() if dw is not None else None,
+                db.data_ptr() if db is not None else None, B, Fin, Fout, K, ws.data_ptr(), ws.numel(),
+                _stream_ptr(x.device),
+            )
+        _lib.check(rc, "dsw_cheb_bwd")
         return dx, dw, db, None
 
 

@@ -78,8 +78,9 @@ int64_t dsw_plan_operand_bytes(const dsw_plan* plan);
  * ConvCheb.forward (layers.py:365-376):
  *     y[b,v,:] = bias + sum_{k<K} (T_k(L) x_b)[v,:] . W[:,k,:],   T_0=I, T_1=L, T_k=2 L T_{k-1}-T_{k-2}
  * W is the reference's parameter layout [Fin][K][Fout] contiguous; bias [Fout] or NULL.
- * act: 0 = none, 1 = ReLU applied after the bias (ConvBlock.forward, my_models_graph.py:104-118).
- * Workspace holds the K-1 intermediate Chebyshev terms.
+ * act: 0 = none, 1 = ReLU applied after the bias (ConvBlock.forward, my_models_graph.py:104-118; only
+ * with the TERMS order, DSW_ERR_UNSUPPORTED otherwise).
+ * Workspace holds the intermediate planes (K-1 Chebyshev terms of x, or K planes x.W_k).
  * ------------------------------------------------------------------------------------------- */
 size_t dsw_cheb_fwd_workspace_bytes(int32_t B, int32_t V, int32_t Fin, int32_t Fout, int32_t K);
 int dsw_cheb_fwd(const dsw_plan* lap, const float* x, int64_t x_sB, int64_t x_sV, const float* W,
@@ -92,20 +93,31 @@ int dsw_cheb_fwd(const dsw_plan* lap, const float* x, int64_t x_sB, int64_t x_sV
 int dsw_cheb_terms(const dsw_plan* lap, const float* x, int64_t x_sB, int64_t x_sV, float* terms,
                    int32_t B, int32_t F, int32_t K, void* stream);
 
-/* Gradient w.r.t. the input (autograd of layers.py:158-177 w.r.t. `inputs`):
- *     dx_b = sum_k T_k(L^T) (dy_b . W[:,k,:]^T)        evaluated by the adjoint (Clenshaw) recurrence.
- * dy is [B][V][Fout] contiguous, dx is written [B][V][Fin] contiguous. */
+/* Which evaluation order the forward / backward will use for these channel counts (1 = TERMS,
+ * 2 = CLENSHAW; see dsw_cheb.cu): the hops run on the side with fewer channels. */
+int dsw_cheb_fwd_algo(int32_t Fin, int32_t Fout, int32_t K);
+int dsw_cheb_bwd_algo(int32_t Fin, int32_t Fout, int32_t K);
+
+/* Backward of the convolution (autograd of layers.py:158-177 and of the bias add :375), both
+ * gradients in one call so that they can share the Chebyshev terms of dy:
+ *     dx_b        = sum_k T_k(L^T) (dy_b . W[:,k,:]^T)                       (dx may be NULL)
+ *     dW[f,k,o]   = sum_{b,v} (T_k(L) x_b)[v,f] dy[b,v,o],  dbias[o] = sum_{b,v} dy[b,v,o]   (dW may be NULL)
+ * dy is [B][V][Fout] contiguous; dx is written [B][V][Fin] contiguous; dW [Fin][K][Fout] is
+ * overwritten; dbias may be NULL.  `saved_terms` = the [K-1][B][V][Fin] Chebyshev terms the forward
+ * left at the start of its workspace (only when dsw_cheb_fwd_algo == 1, dsw_cheb_bwd_algo == 2 and
+ * sample chunking is off), or NULL.  The reduction over (b, v) is a fixed-order two-pass sum:
+ * deterministic. */
+size_t dsw_cheb_bwd_workspace_bytes(int32_t B, int32_t V, int32_t Fin, int32_t Fout, int32_t K,
+                                    int32_t have_saved_terms);
+int dsw_cheb_bwd(const dsw_plan* lap, const float* x, int64_t x_sB, int64_t x_sV, const float* dy,
+                 const float* W, const float* saved_terms, float* dx, float* dW, float* dbias, int32_t B,
+                 int32_t Fin, int32_t Fout, int32_t K, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The two halves on their own (thin wrappers over dsw_cheb_bwd). */
 size_t dsw_cheb_bwd_data_workspace_bytes(int32_t B, int32_t V, int32_t Fin, int32_t Fout, int32_t K);
 int dsw_cheb_bwd_data(const dsw_plan* lap, const float* dy, const float* W, float* dx, int32_t B,
                       int32_t Fin, int32_t Fout, int32_t K, void* workspace, size_t workspace_bytes,
                       void* stream);
-
-/* Gradient w.r.t. weight and bias (autograd of layers.py:176-177 and :375):
- *     dW[f,k,o] = sum_{b,v} (T_k(L) x_b)[v,f] dy[b,v,o],   dbias[o] = sum_{b,v} dy[b,v,o]
- * `saved_terms` = the [K-1][B][V][Fin] Chebyshev terms the forward left at the start of its workspace
- * (valid when sample chunking is off), or NULL to recompute them here (the forward then need not keep
- * its workspace; the reference itself keeps every term alive for autograd).  dW is overwritten
- * ([Fin][K][Fout]); dbias may be NULL.  Deterministic (fixed-order two-pass reduction). */
 size_t dsw_cheb_bwd_weight_workspace_bytes(int32_t B, int32_t V, int32_t Fin, int32_t Fout, int32_t K);
 int dsw_cheb_bwd_weight(const dsw_plan* lap, const float* x, int64_t x_sB, int64_t x_sV,
                         const float* dy, const float* saved_terms, float* dW, float* dbias, int32_t B,
@@ -180,9 +192,11 @@ int dsw_get_mix_mode(void);
 enum {
   DSW_OPT_HOP_KERNEL = 0,    /* 0 = auto (bulk-copy-staged tile kernel), 1 = row-block kernel through L1, 2 = plain CSR, 3 = panel-staged L1 tile kernel */
   DSW_OPT_L2_CHUNK_BYTES = 1, /* working-set budget (bytes) of L2-resident sample chunks; 0 / 1 = chunking off (default) */
-  DSW_OPT_RESERVED2 = 2,
-  DSW_OPT_RESERVED3 = 3,
-  DSW_OPT_COUNT = 4
+  DSW_OPT_DEBUG = 2,          /* timing experiments only (results become wrong): 1 = hops skip staging, 2 = hops skip the FMA loop */
+  DSW_OPT_NO_TMA = 3,         /* 1 = stage tiles with cp.async / register loads instead of tensor-map TMA */
+  DSW_OPT_FWD_ALGO = 4,       /* 0 = auto by channel counts, 1 = TERMS (hops on Fin, then mix), 2 = CLENSHAW (mix, then hops on Fout) */
+  DSW_OPT_BWD_ALGO = 5,       /* 0 = auto, 1 = TERMS (hops on dy, Fout channels), 2 = CLENSHAW (hops on Fin channels) */
+  DSW_OPT_COUNT = 6
 };
 int dsw_set_option(int key, int64_t value);
 int64_t dsw_get_option(int key);

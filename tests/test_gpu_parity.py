@@ -97,8 +97,9 @@ def test_convcheb_matches_oracle_seeded(B, nside, Fin, Fout, K, dev, mix_mode):
 @pytest.mark.parametrize("chunk_bytes", [0, 1 << 20], ids=["nochunk", "chunk1MB"])
 @pytest.mark.parametrize("save_terms", [True, False], ids=["saved-terms", "recompute"])
 def test_hop_kernels_chunking_and_saved_terms_agree(hop_kernel, chunk_bytes, save_terms, dev, lib):
-    """Every hop kernel variant, the L2-resident sample chunking and the saved-terms / recompute
-    weight-gradient paths are the same arithmetic: all must match the oracle."""
+    """Every hop kernel variant, the L2-resident sample chunking, the saved-terms / recompute
+    weight-gradient paths and both evaluation orders (TERMS / CLENSHAW, forward and backward) are the
+    same arithmetic: all must match the oracle."""
     from deepsphere_weather_b200 import functional as F_
     from deepsphere_weather_b200 import graphs as G
     from deepsphere_weather_b200 import layers as L
@@ -116,15 +117,20 @@ def test_hop_kernels_chunking_and_saved_terms_agree(hop_kernel, chunk_bytes, sav
     lib.dsw_set_option(1, chunk_bytes)
     F_.set_save_terms(save_terms)
     try:
-        layer = L.ConvCheb(Fin, Fout, K, lap).to(dev)
-        layer.set_parameters(w.to(dev), b.to(dev))
-        xg = x.to(dev).requires_grad_(True)
-        yg = layer(xg)
-        yg.backward(dy.to(dev))
-        assert rel_err(yg, yo) < REL_TOL
-        assert rel_err(xg.grad, xo.grad) < REL_TOL
-        assert rel_err(layer.weight.grad, wo.grad) < REL_TOL
-        assert rel_err(layer.bias.grad, bo.grad) < REL_TOL
+        for fwd_algo in (1, 2):
+            for bwd_algo in (1, 2):
+                lib.dsw_set_option(4, fwd_algo)
+                lib.dsw_set_option(5, bwd_algo)
+                layer = L.ConvCheb(Fin, Fout, K, lap).to(dev)
+                layer.set_parameters(w.to(dev), b.to(dev))
+                xg = x.to(dev).requires_grad_(True)
+                yg = layer(xg)
+                yg.backward(dy.to(dev))
+                tag = f"fwd_algo={fwd_algo} bwd_algo={bwd_algo}"
+                assert rel_err(yg, yo) < REL_TOL, tag
+                assert rel_err(xg.grad, xo.grad) < REL_TOL, tag
+                assert rel_err(layer.weight.grad, wo.grad) < REL_TOL, tag
+                assert rel_err(layer.bias.grad, bo.grad) < REL_TOL, tag
         # the recurrence alone (layers.py:163-169), restated with torch.sparse.mm on the CPU
         terms = F_.cheb_terms(x.to(dev), F_.plan_for(lap.to(dev)), K)
         x0 = x.permute(1, 2, 0).reshape(V, Fin * B)
@@ -134,9 +140,47 @@ def test_hop_kernels_chunking_and_saved_terms_agree(hop_kernel, chunk_bytes, sav
         for k in range(1, K):
             assert rel_err(terms[k - 1], t[k].reshape(V, Fin, B).permute(2, 0, 1)) < REL_TOL
     finally:
-        lib.dsw_set_option(0, 0)
-        lib.dsw_set_option(1, 0)
+        for key in (0, 1, 4, 5):
+            lib.dsw_set_option(key, 0)
         F_.set_save_terms(True)
+
+
+@pytest.mark.parametrize("fwd_algo,bwd_algo", [(1, 1), (1, 2), (2, 1), (2, 2)])
+def test_evaluation_orders_on_nonsymmetric_operator(fwd_algo, bwd_algo, dev, lib, mix_mode):
+    """Voronoi (cotan) Laplacians are not symmetric (reference layers.py:53-54): the backward must use
+    L^T in both evaluation orders.  Random non-symmetric sparse operator, oracle = torch autograd."""
+    from deepsphere_weather_b200 import layers as L
+    from oracle import cheb_oracle as O
+
+    rng = np.random.default_rng(3)
+    V, B, Fin, Fout, K = 640, 3, 48, 80, 4
+    rows = np.repeat(np.arange(V), 9)
+    cols = (rows + rng.integers(-40, 41, size=rows.size)) % V
+    vals = rng.normal(size=rows.size).astype(np.float32) * 0.15
+    m = sparse.coo_matrix((vals, (rows, cols)), shape=(V, V))
+    m.sum_duplicates()
+    lap = torch.sparse_coo_tensor(np.stack([m.row, m.col]).astype(np.int64), m.data, (V, V)).coalesce()
+    torch.manual_seed(11)
+    x, dy = torch.randn(B, V, Fin), torch.randn(B, V, Fout)
+    w, b = torch.randn(Fin, K, Fout) * 0.05, torch.randn(Fout) * 0.1
+    xo, wo, bo = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yo = O.conv_cheb_layer(lap, xo, wo, bo)
+    yo.backward(dy)
+    lib.dsw_set_option(4, fwd_algo)
+    lib.dsw_set_option(5, bwd_algo)
+    try:
+        layer = L.ConvCheb(Fin, Fout, K, lap).to(dev)
+        layer.set_parameters(w.to(dev), b.to(dev))
+        xg = x.to(dev).requires_grad_(True)
+        yg = layer(xg)
+        yg.backward(dy.to(dev))
+        assert rel_err(yg, yo) < REL_TOL
+        assert rel_err(xg.grad, xo.grad) < REL_TOL
+        assert rel_err(layer.weight.grad, wo.grad) < REL_TOL
+        assert rel_err(layer.bias.grad, bo.grad) < REL_TOL
+    finally:
+        lib.dsw_set_option(4, 0)
+        lib.dsw_set_option(5, 0)
 
 
 def test_convcheb_accepts_strided_views(dev):

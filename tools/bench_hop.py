@@ -51,22 +51,24 @@ def main():
     lib.dsw_set_option(OPT_HOP, 1)
     lib.dsw_set_option(OPT_CHUNK, 1)
     ref = F_.cheb_terms(x, plan, K)
-    configs = [("legacy-rb", 1, 1), ("l1-tile", 3, 1), ("tma", 0, 1), ("tma+chunk(default)", 0, 0)]
-    for mb in (24, 40, 64, 96):
-        configs.append((f"tma+chunk{mb}MB", 0, mb << 20))
+    configs = [("row-block-L1", 1, 1), ("team", 0, 1)]
+    if os.environ.get("DSW_DEBUG_SKIP"):
+        configs += [("team-skip-staging", 0, 1), ("team-skip-compute", 0, 1)]
     for name, hop, chunk in configs:
         lib.dsw_set_option(OPT_HOP, hop)
         lib.dsw_set_option(OPT_CHUNK, chunk)
+        lib.dsw_set_option(2, 1 if name == "team-skip-staging" else 2 if name == "team-skip-compute" else 0)
         out = F_.cheb_terms(x, plan, K)
         err = (out - ref).abs().max().item() / ref.abs().max().item()
         med, best = timed(lambda: F_.cheb_terms(x, plan, K), flush)
         print(f"terms nside{nside} B{B} F{F} K{K} {name:22s} median {med:8.1f} us  best {best:8.1f} us  "
-              f"{alg / med / 1e3:7.1f} GB/s alg  frac {alg / med / 1e3 / 6545.3:.3f}  maxrel-vs-legacy {err:.2e}", flush=True)
+              f"{alg / med / 1e3:7.1f} GB/s alg  frac {alg / med / 1e3 / 6545.3:.3f}  maxrel-vs-rb {err:.2e}", flush=True)
 
     # ConvCheb fwd / fwd+bwd on the same graph (Fin = Fout = F)
     layer = L.ConvCheb(F, F, K, lap).to(dev)
     xg = x.clone().requires_grad_(True)
-    for name, hop, chunk in [("legacy-rb", 1, 1), ("tma", 0, 1), ("tma+chunk(default)", 0, 0)]:
+    lib.dsw_set_option(2, 0)
+    for name, hop, chunk in [("row-block-L1", 1, 1), ("team", 0, 1)]:
         lib.dsw_set_option(OPT_HOP, hop)
         lib.dsw_set_option(OPT_CHUNK, chunk)
         with torch.no_grad():
