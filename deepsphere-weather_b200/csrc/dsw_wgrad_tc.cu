@@ -18,6 +18,7 @@
 #include <algorithm>
 
 #include "dsw_internal.cuh"
+#include "dsw_tmap.cuh"
 
 namespace dsw {
 
@@ -361,6 +362,282 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
   if (warp == 16) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA-fed variant (production path for 16-byte aligned operands).
+//
+// Every unit (64 rows x 64 channels of fp32 = 16 KB) is landed in the stage by one tensor-map TMA box
+// issued by a producer lane (zero fill past the row range / channel count), up to S stages ahead of
+// the arithmetic; the converters read the raw unit from shared memory and overwrite it in place with
+// its bf16 hi (first 8 KB) and lo (second 8 KB) MN-major SWIZZLE_128B images, so consecutive 64-channel
+// blocks of one operand are 16 KB apart (the descriptors' LBO).
+//
+//   warps 0-7 converters (+ epilogue) | warp 8 producer | warp 9 MMA issuer
+// ---------------------------------------------------------------------------------------------
+constexpr int UNIT = 64 * 64 * 4;       // bytes of one raw unit = its two bf16 images
+constexpr int T_CONV = 256;
+constexpr int T_THREADS = T_CONV + 64;
+
+struct WtmaArgs {
+  WtcArgs c;
+  int32_t stages;
+  int32_t rank;                       // 2: Fin-side rows are the flat (b, v) index; 3: (f, v, b) coordinates
+  CUtensorMap maps[DSW_MAX_K + 1];    // Fin-side planes first (Ka of them), then the Fout-side planes (Kb)
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_constant__ WtmaArgs Q) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ float bias_acc[256];
+  const WtcArgs& P = Q.c;
+  const WgradArgs& a = P.w;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int BN = P.BN, nb = P.nb, S = Q.stages;
+  const int U = 2 + nb;  // units per row block: A half 0, A half 1, B blocks
+  const uint32_t stage_bytes = (uint32_t)U * UNIT;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bars = smem_base + (uint32_t)S * stage_bytes;
+  auto raw_full = [&](int s) { return bars + 8u * s; };
+  auto full = [&](int s) { return bars + 8u * (S + s); };
+  auto empty = [&](int s) { return bars + 8u * (2 * S + s); };
+  const uint32_t tmem_slot = bars + 8u * (3 * S);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (size_t)S * stage_bytes + 8 * (3 * S));
+
+  const int mtile = blockIdx.x, split = blockIdx.z;
+  const int kb_plane = blockIdx.y / P.otiles, ntile = blockIdx.y - kb_plane * P.otiles;
+  const int n_half = a.Ka * P.ftiles;
+  const int64_t r_begin = (int64_t)split * P.kb_per_split * KB;
+  const int64_t r_end = (r_begin + (int64_t)P.kb_per_split * KB < a.N) ? r_begin + (int64_t)P.kb_per_split * KB : a.N;
+  const int nkb = (r_end > r_begin) ? (int)((r_end - r_begin + KB - 1) / KB) : 0;
+  const int o_base = ntile * BN;
+  const bool half_ok[2] = {mtile * 2 < n_half, mtile * 2 + 1 < n_half};
+
+  if (t == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(raw_full(s), 1);
+      mbar_init(full(s), T_CONV);
+      mbar_init(empty(s), 1);
+    }
+    fence_mbar_init();
+  }
+  if (t < 256) bias_acc[t] = 0.f;
+  // a missing second half-tile is never loaded: keep its images zero in every stage
+  if (!half_ok[1])
+    for (int s = 0; s < S; ++s)
+      for (int i = t; i < UNIT / 16; i += T_THREADS)
+        *reinterpret_cast<uint4*>(smem_gen + (size_t)s * stage_bytes + UNIT + i * 16) = make_uint4(0, 0, 0, 0);
+  if (warp == 9) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp < 8) {
+    // ================= converters =================
+    const int q = t & 15, r0 = t >> 4;  // float4 column, rows r0 + 16 i
+    const bool do_bias = (mtile == 0) && (kb_plane == 0) && (a.dbias != nullptr);
+    float4 bsum[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bsum[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % S;
+      const uint32_t ph = (uint32_t)(kb / S) & 1;
+      uint8_t* st = smem_gen + (size_t)s * stage_bytes;
+      mbar_wait(raw_full(s), ph);
+      float4 v[6][4];
+#pragma unroll
+      for (int u = 0; u < 6; ++u)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          v[u][i] = (u < U && (u != 1 || half_ok[1]))
+                        ? *reinterpret_cast<const float4*>(st + u * UNIT + (r0 + 16 * i) * 256 + q * 16)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      asm volatile("bar.sync 1, %0;" ::"n"(T_CONV) : "memory");  // every converter has read its share
+#pragma unroll
+      for (int u = 0; u < 6; ++u) {
+        if (u >= U || (u == 1 && !half_ok[1])) continue;
+        uint8_t* hi_img = st + u * UNIT;
+        uint8_t* lo_img = hi_img + UNIT / 2;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t row = r0 + 16 * i;
+          __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+          split_bf16(v[u][i].x, h0, l0);
+          split_bf16(v[u][i].y, h1, l1);
+          split_bf16(v[u][i].z, h2, l2);
+          split_bf16(v[u][i].w, h3, l3);
+          const uint32_t off = swz(row, q >> 1) + (q & 1) * 8;
+          *reinterpret_cast<uint2*>(hi_img + off) = make_uint2(pack2(h0, h1), pack2(h2, h3));
+          *reinterpret_cast<uint2*>(lo_img + off) = make_uint2(pack2(l0, l1), pack2(l2, l3));
+        }
+        if (do_bias && u >= 2) {
+          float4& b = bsum[u - 2];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) b.x += v[u][i].x, b.y += v[u][i].y, b.z += v[u][i].z, b.w += v[u][i].w;
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(full(s));
+    }
+
+    // ---- dbias partial (fp32, CTA-local reduction through shared memory) ----
+    if (do_bias) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < nb) {
+          atomicAdd(&bias_acc[j * 64 + q * 4 + 0], bsum[j].x);
+          atomicAdd(&bias_acc[j * 64 + q * 4 + 1], bsum[j].y);
+          atomicAdd(&bias_acc[j * 64 + q * 4 + 2], bsum[j].z);
+          atomicAdd(&bias_acc[j * 64 + q * 4 + 3], bsum[j].w);
+        }
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(T_CONV) : "memory");
+
+    // ================= epilogue: TMEM -> partial[split] =================
+    const int64_t prow = (int64_t)a.K * a.Fin + 1;
+    float* __restrict__ Pp = a.partial + (int64_t)split * prow * a.Fout;
+    if (do_bias && t < BN && o_base + t < a.Fout) Pp[(prow - 1) * a.Fout + o_base + t] = bias_acc[t];
+
+    if (nkb > 0) {
+      const int last = nkb - 1;
+      mbar_wait(empty(last % S), (uint32_t)(last / S) & 1);
+      tc_fence_after();
+    }
+    const int quarter = warp & 3, part = warp >> 2;  // 4 lane quarters x 2 column parts
+    const int L = quarter * 32 + lane;
+    const int h = L >> 6, fl = L & 63;
+    const int ht = mtile * 2 + h;
+    int64_t m = -1;
+    if (ht < n_half) {
+      const int k = ht / P.ftiles, f0 = (ht - k * P.ftiles) * 64;
+      if (f0 + fl < a.Fin) m = (int64_t)(f0 + fl) * a.K + k + kb_plane;
+    }
+    const int chunks = BN / 16;
+    for (int ch = (chunks * part) / 2; ch < (chunks * (part + 1)) / 2; ++ch) {
+      uint32_t r[16];
+      if (nkb > 0) {
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 16), r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) r[e] = 0u;
+      }
+      if (m < 0) continue;
+      const int o0 = o_base + ch * 16;
+      if (o0 + 15 < a.Fout && (a.Fout & 3) == 0) {
+#pragma unroll
+        for (int e = 0; e < 16; e += 4)
+          *reinterpret_cast<uint4*>(Pp + m * a.Fout + o0 + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (o0 + e < a.Fout) Pp[m * a.Fout + o0 + e] = __uint_as_float(r[e]);
+      }
+    }
+  } else if (warp == 8) {
+    // ================= producer (one thread): one TMA box per unit =================
+    if (lane == 0) {
+      int hk[2], hf[2];
+      for (int h = 0; h < 2; ++h) {
+        const int ht = mtile * 2 + h;
+        hk[h] = half_ok[h] ? ht / P.ftiles : 0;
+        hf[h] = half_ok[h] ? (ht - hk[h] * P.ftiles) * 64 : 0;
+      }
+      const CUtensorMap* ymap = &Q.maps[a.Ka + kb_plane];
+      const uint32_t tx = (uint32_t)((half_ok[1] ? 2 : 1) + nb) * UNIT;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % S;
+        const uint32_t use = (uint32_t)(kb / S);
+        if (use > 0) mbar_wait(empty(s), (use - 1) & 1);
+        const uint32_t st = smem_base + s * stage_bytes;
+        const int64_t n0 = r_begin + (int64_t)kb * KB;
+        mbar_expect_tx(raw_full(s), tx);
+        for (int h = 0; h < 2; ++h) {
+          if (!half_ok[h]) continue;
+          if (Q.rank == 2) {
+            tma_load_2d(st + h * UNIT, &Q.maps[hk[h]], hf[h], (int)n0, raw_full(s));
+          } else {
+            const int bb = (int)(n0 / a.rows_per_batch);
+            tma_load_3d(st + h * UNIT, &Q.maps[hk[h]], hf[h], (int)(n0 - (int64_t)bb * a.rows_per_batch), bb, raw_full(s));
+          }
+        }
+        for (int j = 0; j < nb; ++j) tma_load_2d(st + (2 + j) * UNIT, ymap, o_base + 64 * j, (int)n0, raw_full(s));
+      }
+    }
+  } else if (lane == 0) {
+    // ================= MMA issuer =================
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t lbo = (uint32_t)UNIT;  // between 64-channel blocks (each unit = [hi | lo])
+    const uint32_t sbo = 1024u;           // between 8-row groups
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % S;
+      mbar_wait(full(s), (uint32_t)(kb / S) & 1);
+      tc_fence_after();
+      const uint32_t st = smem_base + s * stage_bytes;
+      const uint32_t Ah = st, Al = st + UNIT / 2, Bh = st + 2u * UNIT, Bl = Bh + UNIT / 2;
+      for (int ks = 0; ks < KB / 16; ++ks) {
+        const uint32_t adv = (uint32_t)ks * 2048u;  // 16 rows = two 8-row groups
+        const uint64_t dAh = make_desc_mn(Ah + adv, lbo, sbo), dAl = make_desc_mn(Al + adv, lbo, sbo);
+        const uint64_t dBh = make_desc_mn(Bh + adv, lbo, sbo), dBl = make_desc_mn(Bl + adv, lbo, sbo);
+        umma_bf16(tmem_base, dAh, dBh, idesc, (kb | ks) != 0);
+        umma_bf16(tmem_base, dAh, dBl, idesc, 1u);
+        umma_bf16(tmem_base, dAl, dBh, idesc, 1u);
+      }
+      umma_commit(empty(s));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+}
+
+static int tma_stages_for(int nb) {
+  const size_t stage = (size_t)(2 + nb) * UNIT;
+  const int s = (int)((224 * 1024) / stage);
+  return std::max(1, std::min(s, 4));
+}
+static size_t tma_smem_bytes_for(int nb) { return (size_t)tma_stages_for(nb) * (2 + nb) * UNIT + 1024 + 256; }
+
+// Tensor maps: box = [64 channels x 64 rows] of fp32.  Returns false when the operands do not allow it.
+static bool encode_maps(const WgradArgs& a, WtmaArgs* Q) {
+  if ((a.Fin & 3) || (a.Fout & 3)) return false;
+  const int64_t V = a.rows_per_batch;
+  const int64_t B = (a.N + V - 1) / V;
+  bool flat = true;
+  for (int k = 0; k < a.Ka; ++k) {
+    if ((reinterpret_cast<uintptr_t>(a.T[k]) & 15) || (a.t_sV[k] & 3) || (a.t_sB[k] & 3) || a.t_sV[k] < a.Fin) return false;
+    flat = flat && (a.t_sB[k] == V * a.t_sV[k] || B == 1);
+  }
+  if (!flat && (V % KB != 0)) return false;
+  Q->rank = flat ? 2 : 3;
+  const uint32_t box[3] = {64u, (uint32_t)KB, 1u};
+  for (int k = 0; k < a.Ka; ++k) {
+    uint64_t dims[3], strides[2];
+    dims[0] = (uint64_t)a.Fin;
+    if (flat) {
+      dims[1] = (uint64_t)a.N, strides[0] = (uint64_t)a.t_sV[k] * 4;
+    } else {
+      dims[1] = (uint64_t)V, dims[2] = (uint64_t)B;
+      strides[0] = (uint64_t)a.t_sV[k] * 4, strides[1] = (uint64_t)a.t_sB[k] * 4;
+    }
+    if (!encode_f32_map(&Q->maps[k], a.T[k], flat ? 2 : 3, dims, strides, box)) return false;
+  }
+  for (int k = 0; k < a.Kb; ++k) {
+    if (reinterpret_cast<uintptr_t>(a.Y[k]) & 15) return false;
+    const uint64_t dims[2] = {(uint64_t)a.Fout, (uint64_t)a.N};
+    const uint64_t strides[1] = {(uint64_t)a.Fout * 4};
+    if (!encode_f32_map(&Q->maps[a.Ka + k], a.Y[k], 2, dims, strides, box)) return false;
+  }
+  return true;
+}
+
 static size_t smem_bytes_for(int nb) { return (size_t)STAGES * (2 * 2 * BLK + 2 * nb * BLK) + 1024 + 64; }
 
 }  // namespace wtc
@@ -405,12 +682,24 @@ int launch_wgrad_tc(const WgradArgs& a, size_t partial_bytes, cudaStream_t st) {
   while (cols < P.BN) cols <<= 1;
   P.tmem_cols = cols;
 
+  dim3 grid(mtiles, ntiles, nsplit);
+  if (g_options[DSW_OPT_NO_TMA].load(std::memory_order_relaxed) == 0 && wtc::tma_stages_for(P.nb) >= 2) {
+    wtc::WtmaArgs Q;
+    Q.c = P;
+    Q.stages = wtc::tma_stages_for(P.nb);
+    if (wtc::encode_maps(a, &Q)) {
+      static std::atomic<bool> attr_tma{false};
+      if (!attr_tma.exchange(true))
+        DSW_CUDA_TRY(cudaFuncSetAttribute(wtc::wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      wtc::wgrad_tma_kernel<<<grid, wtc::T_THREADS, wtc::tma_smem_bytes_for(P.nb), st>>>(Q);
+      return check_launch();
+    }
+  }
   const size_t smem = wtc::smem_bytes_for(P.nb);
   static std::atomic<bool> attr_set{false};
   if (!attr_set.exchange(true))
     DSW_CUDA_TRY(cudaFuncSetAttribute(wtc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)wtc::smem_bytes_for(4)));  // + 1 KB static bias_acc <= 227 KB
-  dim3 grid(mtiles, ntiles, nsplit);
   wtc::wgrad_tc_kernel<<<grid, wtc::THREADS, smem, st>>>(P);
   return check_launch();
 }
