@@ -326,6 +326,9 @@ struct TeamHopPlan {
   int32_t debug_skip;     // timing experiments only: 1 = skip staging, 2 = skip the entry loop
 };
 
+// Phase timing for tuning (DSW_OPT_DEBUG = 4): cycles summed over teams, read back by dsw_debug_counters.
+__device__ unsigned long long g_hop_prof[8];
+
 struct HopMaps {
   CUtensorMap m[8];  // box rows 1, 2, 4, .. 128 over the gather source [B][n_cols][F]
 };
@@ -437,20 +440,27 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1)
   uint32_t phase = 0;
   const int item_begin = blockIdx.y * P.items_per_cta;
   const int item_end = min(item_begin + P.items_per_cta, P.n_items);
-  for (int item = item_begin + team; item < item_end; item += P.n_teams) {
+  // Stages the source rows of one item into the team's buffer.  TMA: issued by the lanes of the team's
+  // first warp; called for the first item before the loop and for the next item as soon as the entry
+  // loop of the current one is done (the buffer is free then), so that the transfer overlaps the
+  // output stores and the next item's Z / G loads.
+  auto stage = [&](int item) {
     const int b = item / P.n_slabs, slab = item - b * P.n_slabs;
-    const int slab_f = min(64, a.F - slab * 64);       // channels in this slab (multiple of 4)
-    const int cpr = slab_f >> 2;                        // 16-byte chunks per row
-    // ---- stage the tile's source rows for this item ----
+    const int slab_f = min(64, a.F - slab * 64);
+    const int cpr = slab_f >> 2;
+    (void)cpr;
     if (TMA && P.debug_skip == 1) {
     } else if (TMA) {
       // one lane issues a tensor-map box per piece (run of consecutive source rows); the copies bypass
       // registers and L1, complete on the team's mbarrier, and out-of-range channels are zero-filled
-      if (tt == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (tt < 32) {
         const uint32_t bar = hop_smem_u32(s_bar + team);
-        hop_mbar_expect_tx(bar, (uint32_t)nrows * 256u);
-        for (int i = 0; i < npieces; ++i) {
+        if (tt == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          hop_mbar_expect_tx(bar, (uint32_t)nrows * 256u);
+        }
+        __syncwarp();
+        for (int i = tt; i < npieces; i += 32) {  // the lanes of the first warp issue the boxes in parallel
           const uint32_t meta = s_meta[i];
           tma_load_3d(xs_u32 + (meta >> 8) * 256u, &maps.m[meta & 7u], slab * 64, s_row[i], b, bar);
         }
@@ -469,8 +479,20 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1)
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
+  };
+  if (TMA && item_begin + team < item_end) stage(item_begin + team);
+
+  for (int item = item_begin + team; item < item_end; item += P.n_teams) {
+    const int b = item / P.n_slabs, slab = item - b * P.n_slabs;
+    const int slab_f = min(64, a.F - slab * 64);       // channels in this slab (multiple of 4)
+    const int cpr = slab_f >> 2;                        // 16-byte chunks per row
+    const bool prof = (P.debug_skip == 4) && (tt == 0);
+    long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    if (prof) t0 = clock64();
+    if (!TMA) stage(item);
     // Accumulators start at (beta * Z + G) / alpha (alpha is 1 or 2, so the scaling is exact): the
     // loads are issued here, behind the cp.asyncs, and land while the tile is being staged.
+    if (prof) t1 = clock64();
     float4 acc[4][4];
     {
       const float inv_alpha = 1.f / a.alpha;
@@ -524,6 +546,7 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1)
       team_sync(team);
     }
 
+    if (prof) t2 = clock64();
     {
       auto load_x = [&](uint32_t o, float4(&x)[4]) {
         x[0] = *reinterpret_cast<const float4*>(xA + o);
@@ -551,6 +574,12 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1)
       }
     }
 
+    if (TMA) {
+      // every lane of the team is done reading the staged rows: the next item's transfer may start
+      team_sync(team);
+      if (item + P.n_teams < item_end) stage(item + P.n_teams);
+    }
+    if (prof) t3 = clock64();
     // ---- epilogue: O = alpha * acc ----
     if (active) {
 #pragma unroll
@@ -567,7 +596,15 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1)
       }
     }
     // every lane of the team is done reading the staged rows before the next item overwrites them
-    team_sync(team);
+    if (!TMA) team_sync(team);
+    if (prof) {
+      const long long t4 = clock64();
+      atomicAdd(&g_hop_prof[0], (unsigned long long)(t1 - t0));  // issue staging
+      atomicAdd(&g_hop_prof[1], (unsigned long long)(t2 - t1));  // Z / G loads + wait for the tile
+      atomicAdd(&g_hop_prof[2], (unsigned long long)(t3 - t2));  // entry loop
+      atomicAdd(&g_hop_prof[3], (unsigned long long)(t4 - t3));  // stores + team barrier
+      atomicAdd(&g_hop_prof[4], 1ull);                           // items
+    }
   }
 }
 
@@ -602,6 +639,7 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
       P.n_slabs = ceil_div(a.F, 64);
       P.n_items = a.B * P.n_slabs;
       n_teams = std::min(n_teams, P.n_items);
+      if (g_options[DSW_OPT_DEBUG].load(std::memory_order_relaxed) == 3) n_teams = std::min(n_teams, 2);
       P.n_teams = n_teams;
       P.debug_skip = (int)g_options[DSW_OPT_DEBUG].load(std::memory_order_relaxed);
       // items per CTA: a few per team to amortise the staged panels, while keeping >= ~3 waves of CTAs
@@ -689,6 +727,18 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
 using namespace dsw;
 
 extern "C" {
+
+int dsw_debug_counters(uint64_t* out8, int reset) {
+  if (!out8) return DSW_ERR_BAD_ARGUMENT;
+  unsigned long long h[8];
+  DSW_CUDA_TRY(cudaMemcpyFromSymbol(h, g_hop_prof, sizeof(h)));
+  for (int i = 0; i < 8; ++i) out8[i] = h[i];
+  if (reset) {
+    unsigned long long z[8] = {};
+    DSW_CUDA_TRY(cudaMemcpyToSymbol(g_hop_prof, z, sizeof(z)));
+  }
+  return DSW_OK;
+}
 
 int dsw_spmm_fwd(const dsw_plan* mat, const float* x, int64_t x_sB, int64_t x_sV, float* y, int32_t B,
                  int32_t F, void* stream) {

@@ -198,6 +198,9 @@ enum {
   DSW_OPT_BWD_ALGO = 5,       /* 0 = auto, 1 = TERMS (hops on dy, Fout channels), 2 = CLENSHAW (hops on Fin channels) */
   DSW_OPT_COUNT = 6
 };
+/* Tuning only: with DSW_OPT_DEBUG = 4 the hop kernel sums per-phase SM cycles over its teams
+ * (issue staging, wait for tile + Z/G, entry loop, stores, item count). */
+int dsw_debug_counters(uint64_t* out8, int reset);
 int dsw_set_option(int key, int64_t value);
 int64_t dsw_get_option(int key);
 

@@ -53,16 +53,33 @@ def main():
     ref = F_.cheb_terms(x, plan, K)
     configs = [("row-block-L1", 1, 1), ("team", 0, 1)]
     if os.environ.get("DSW_DEBUG_SKIP"):
-        configs += [("team-skip-staging", 0, 1), ("team-skip-compute", 0, 1)]
+        configs += [("team-skip-staging", 0, 1), ("team-skip-compute", 0, 1), ("team-2teams", 0, 1)]
     for name, hop, chunk in configs:
         lib.dsw_set_option(OPT_HOP, hop)
         lib.dsw_set_option(OPT_CHUNK, chunk)
-        lib.dsw_set_option(2, 1 if name == "team-skip-staging" else 2 if name == "team-skip-compute" else 0)
+        lib.dsw_set_option(2, 1 if name == "team-skip-staging" else 2 if name == "team-skip-compute" else 3 if name == "team-2teams" else 0)
         out = F_.cheb_terms(x, plan, K)
         err = (out - ref).abs().max().item() / ref.abs().max().item()
         med, best = timed(lambda: F_.cheb_terms(x, plan, K), flush)
         print(f"terms nside{nside} B{B} F{F} K{K} {name:22s} median {med:8.1f} us  best {best:8.1f} us  "
               f"{alg / med / 1e3:7.1f} GB/s alg  frac {alg / med / 1e3 / 6545.3:.3f}  maxrel-vs-rb {err:.2e}", flush=True)
+
+    if os.environ.get("DSW_DEBUG_SKIP"):
+        import ctypes
+        buf = (ctypes.c_uint64 * 8)()
+        lib.dsw_set_option(OPT_HOP, 0)
+        lib.dsw_set_option(OPT_CHUNK, 1)
+        lib.dsw_set_option(2, 4)
+        F_.cheb_terms(x, plan, K)
+        torch.cuda.synchronize()
+        lib.dsw_debug_counters(buf, 1)
+        F_.cheb_terms(x, plan, K)
+        torch.cuda.synchronize()
+        lib.dsw_debug_counters(buf, 1)
+        n = max(buf[4], 1)
+        print("phase cycles per item (avg over teams): issue %.0f  wait(tile+Z) %.0f  loop %.0f  store+sync %.0f  items %d" %
+              (buf[0] / n, buf[1] / n, buf[2] / n, buf[3] / n, buf[4]), flush=True)
+        lib.dsw_set_option(2, 0)
 
     # ConvCheb fwd / fwd+bwd on the same graph (Fin = Fout = F)
     layer = L.ConvCheb(F, F, K, lap).to(dev)
