@@ -39,6 +39,9 @@ SIGNATURES = {
     "dsw_cheb_bwd_data": (C.c_int, [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _sz, _ptr]),
     "dsw_cheb_bwd_weight_workspace_bytes": (_sz, [_i32] * 5),
     "dsw_cheb_bwd_weight": (C.c_int, [_ptr, _ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _sz, _ptr]),
+    "dsw_linear_workspace_bytes": (_sz, [_i32] * 4),
+    "dsw_linear_fwd": (C.c_int, [_ptr, _i64, _i64, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _sz, _ptr]),
+    "dsw_linear_bwd": (C.c_int, [_ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _sz, _ptr]),
     "dsw_spmm_fwd": (C.c_int, [_ptr, _ptr, _i64, _i64, _ptr, _i32, _i32, _ptr]),
     "dsw_spmm_bwd": (C.c_int, [_ptr, _ptr, _i64, _i64, _ptr, _i32, _i32, _ptr]),
     "dsw_maxval_pool_fwd": (C.c_int, [_ptr, _ptr, _i64, _i64, _ptr, _ptr, _ptr, _i32, _i32, _ptr]),

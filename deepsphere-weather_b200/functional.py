@@ -216,6 +216,63 @@ def cheb_terms(x: torch.Tensor, plan: SparsePlan, K: int) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------
+# Per-node linear map (ResBlock skip connection)          reference my_models_graph.py:196-201, 214
+# --------------------------------------------------------------------------------------------
+
+
+class NodeLinearFunction(torch.autograd.Function):
+    """``y = x @ W^T + b`` on ``[B, V, Fin]`` with torch.nn.Linear's parameter layout, through the
+    tcgen05 channel-mix / weight-gradient kernels (``dsw_linear_*``)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        _require_cuda_f32(x, "x")
+        _require_cuda_f32(weight, "weight")
+        B, V, Fin = x.shape
+        Fout, Fin_w = weight.shape
+        if Fin != Fin_w:
+            raise ValueError(f"input has {Fin} features but the linear layer expects {Fin_w}")
+        lib = _lib.load()
+        x = x.contiguous()
+        w = weight.contiguous()
+        bptr = bias.contiguous().data_ptr() if bias is not None else None
+        y = torch.empty((B, V, Fout), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            ws = _workspace(lib.dsw_linear_workspace_bytes(B, V, Fin, Fout), x.device)
+            rc = lib.dsw_linear_fwd(x.data_ptr(), x.stride(0), x.stride(1), w.data_ptr(), bptr, y.data_ptr(), B, V, Fin,
+                                    Fout, ws.data_ptr(), ws.numel(), _stream_ptr(x.device))
+        _lib.check(rc, "dsw_linear_fwd")
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        lib = _lib.load()
+        B, V, Fin = x.shape
+        Fout = w.shape[0]
+        dy = dy.contiguous()
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need_db = ctx.has_bias and ctx.needs_input_grad[2]
+        dx = torch.empty_like(x) if need_dx else None
+        dw = torch.empty_like(w) if need_dw else None
+        db = torch.empty(Fout, dtype=torch.float32, device=x.device) if need_db else None
+        if need_dx or need_dw or need_db:
+            with torch.cuda.device(x.device):
+                ws = _workspace(lib.dsw_linear_workspace_bytes(B, V, Fin, Fout), x.device)
+                rc = lib.dsw_linear_bwd(
+                    x.data_ptr(), x.stride(0), x.stride(1), dy.data_ptr(), w.data_ptr(),
+                    dx.data_ptr() if dx is not None else None, dw.data_ptr() if dw is not None else None,
+                    db.data_ptr() if db is not None else None, B, V, Fin, Fout, ws.data_ptr(), ws.numel(),
+                    _stream_ptr(x.device),
+                )
+            _lib.check(rc, "dsw_linear_bwd")
+        return dx, dw, db
+
+
+# --------------------------------------------------------------------------------------------
 # Sparse remap                                                     reference layers.py:956-964
 # --------------------------------------------------------------------------------------------
 

@@ -113,6 +113,17 @@ class ConvCheb(torch.nn.Module):
         return F_.cheb_conv(inputs, self.weight, self.bias, F_.plan_for(self.laplacian))
 
 
+class NodeLinear(torch.nn.Linear):
+    """``torch.nn.Linear`` (same parameters, initialisation and state-dict keys) whose forward /
+    backward on ``[B, V, F]`` node features run on the tcgen05 kernels — the ResBlock skip connection
+    of the reference (``my_models_graph.py:196-201``).  Other input ranks fall through to torch."""
+
+    def forward(self, x):
+        if x.dim() == 3 and x.is_cuda and x.dtype == torch.float32:
+            return F_.NodeLinearFunction.apply(x, self.weight, self.bias)
+        return super().forward(x)
+
+
 # ------------------------------------------------------------------------------------------
 # Nested-order (HEALPix) pools                                    reference layers.py:784-941
 # ------------------------------------------------------------------------------------------

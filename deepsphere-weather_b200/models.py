@@ -28,6 +28,7 @@ def _default_backend():
 
     return SimpleNamespace(
         ConvCheb=L.ConvCheb,
+        Linear=L.NodeLinear,
         healpix_pools={"max": (L.HealpixMaxPool, L.HealpixMaxUnpool), "avg": (L.HealpixAvgPool, L.HealpixAvgUnpool)},
         general_pools=L.PoolUnpoolBlock.getGeneralPoolUnpoolLayer,
     )
@@ -90,7 +91,8 @@ class ResBlock(torch.nn.Module):
         if in_channels == widths[-1]:
             self.res_connection = torch.nn.Identity()
         else:
-            self.res_connection = torch.nn.Linear(in_channels, widths[-1])
+            backend = convblock_kwargs.get("backend") or _default_backend()
+            self.res_connection = getattr(backend, "Linear", torch.nn.Linear)(in_channels, widths[-1])
         if self.rezero:
             self.rezero_weight = torch.nn.Parameter(torch.zeros(1), requires_grad=True)
         if convblock_kwargs.get("batch_norm", False):

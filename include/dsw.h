@@ -125,6 +125,20 @@ int dsw_cheb_bwd_weight(const dsw_plan* lap, const float* x, int64_t x_sB, int64
                         void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Per-node linear map  y[b,v,:] = x[b,v,:] . Wl^T + bias  (Wl[Fout][Fin], torch.nn.Linear layout) and
+ * its gradients: the skip connection of the reference's ResBlock (my_models_graph.py:196-201, :214),
+ * on the same tensor-core kernels as the channel mix.  dx / dW / dbias may each be NULL; x must be
+ * contiguous for dW.  Deterministic.
+ * ------------------------------------------------------------------------------------------- */
+size_t dsw_linear_workspace_bytes(int32_t B, int32_t V, int32_t Fin, int32_t Fout);
+int dsw_linear_fwd(const float* x, int64_t x_sB, int64_t x_sV, const float* Wl, const float* bias,
+                   float* y, int32_t B, int32_t V, int32_t Fin, int32_t Fout, void* workspace,
+                   size_t workspace_bytes, void* stream);
+int dsw_linear_bwd(const float* x, int64_t x_sB, int64_t x_sV, const float* dy, const float* Wl,
+                   float* dx, float* dW, float* dbias, int32_t B, int32_t V, int32_t Fin, int32_t Fout,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Sparse remap (interpolation pooling / unpooling).  Replaces RemapBlock.forward
  * (modules/layers.py:956-964) and its autograd:
  *     fwd: y[b,r,:]  = sum_c M[r,c] x[b,c,:]        x [B][n_cols][F] (strided), y [B][n_rows][F]

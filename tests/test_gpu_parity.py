@@ -468,3 +468,26 @@ def test_full_size_pool_round_trips(dev):
     # pool(unpool(y)) == y  (pool @ unpool = I)
     assert torch.equal(L.HealpixMaxPool(4)(up)[0], torch.maximum(ym, torch.zeros_like(ym)))
     assert rel_err(L.HealpixAvgPool(4)(L.HealpixAvgUnpool(4)(ya))[0], ya) < 1e-6
+
+
+@pytest.mark.parametrize("B,V,Fin,Fout", [(3, 768, 21, 128), (2, 640, 128, 256), (2, 200, 64, 2), (1, 130, 7, 5)])
+def test_node_linear_matches_torch(B, V, Fin, Fout, dev, mix_mode):
+    """The ResBlock skip connection (reference my_models_graph.py:196-201 uses torch.nn.Linear) on the
+    tensor-core kernels: same parameters, outputs and gradients as torch.nn.Linear on the CPU."""
+    from deepsphere_weather_b200 import layers as L
+
+    torch.manual_seed(Fin * 31 + Fout)
+    ref = torch.nn.Linear(Fin, Fout)
+    x, dy = torch.randn(B, V, Fin), torch.randn(B, V, Fout)
+    xo = x.clone().requires_grad_(True)
+    ref(xo).backward(dy)
+    lin = L.NodeLinear(Fin, Fout)
+    lin.load_state_dict(ref.state_dict())
+    lin = lin.to(dev)
+    xg = x.to(dev).requires_grad_(True)
+    yg = lin(xg)
+    yg.backward(dy.to(dev))
+    assert rel_err(yg, ref(x)) < REL_TOL
+    assert rel_err(xg.grad, xo.grad) < REL_TOL
+    assert rel_err(lin.weight.grad, ref.weight.grad) < REL_TOL
+    assert rel_err(lin.bias.grad, ref.bias.grad) < REL_TOL
