@@ -197,9 +197,15 @@ def time_kernel_rooflines(device, hbm_gbs, bf16_tflops):
     alg_bytes = 4 * B * V * F * K + plan.operand_bytes  # x read + K-1 terms written ... per stage
     per_launch_bytes = alg_bytes / n_launch
     achieved = alg_bytes / t / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the three hop launches in
+    # profiles/r01h_hop_team_kernel_ncu.txt (one `ncu --set full` capture of this same call):
+    # (458.4 + 363.2) + (868.3 + 373.9) + (868.5 + 374.1) MB over 3 launches.  Each unfused hop moves
+    # ~3 planes (gather source, k-2 term, output) where the K-plane accounting counts 4/3.
+    ncu_traffic_bytes_per_launch = 1102.1e6
     out["roofline"] = {
-        "kernel": "hop_rb_kernel (Chebyshev SpMM hop), dsw_cheb_terms nside64 B32 F64 K4", "bound": "hbm",
-        "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs, "traffic": None,
+        "kernel": "hop_team_kernel (Chebyshev SpMM hop), dsw_cheb_terms nside64 B32 F64 K4", "bound": "hbm",
+        "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
+        "traffic": ncu_traffic_bytes_per_launch,
         "launches": n_launch, "us_per_launch": t / n_launch * 1e6, "algorithmic_bytes_per_launch": per_launch_bytes,
     }
     del x, lap

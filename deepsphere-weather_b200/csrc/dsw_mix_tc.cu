@@ -8,15 +8,11 @@
 // three tcgen05.mma per K-step accumulate into one fp32 TMEM tile; the dropped a_lo*b_lo term and the
 // second-order rounding leave a relative error of a few 1e-6 per product (parity bar: 1e-4).
 //
-// CTA = one 128-row x BN-column output tile (BN <= 256, TMEM accumulator 128 lanes x BN columns).
-//   warps 0-7  converters: fp32 A rows (global, coalesced float4) -> bf16 hi/lo -> shared memory in the
-//              UMMA canonical K-major SWIZZLE_128B layout; afterwards the epilogue
-//              (tcgen05.ld -> +bias / ReLU -> global).
-//   warp 8     one elected lane: bulk-async copy (TMA, cp.async.bulk) of the pre-split B block into
-//              shared memory, tcgen05.mma issue, tcgen05.commit onto the stage's "empty" mbarrier.
-// Two-stage ring per CTA; with BN <= 64 two CTAs share an SM so one CTA's epilogue overlaps the other's
-// main loop.  B (the weights) is split and laid out as ready-to-copy shared-memory images by a small
-// prep kernel once per call.
+// Two kernels (see the comments above each): mix_tma_kernel, the production path — persistent,
+// warp-specialised, the fp32 A operand landed by tensor-map TMA and converted to bf16 hi / lo in place
+// — and mix_tc_kernel, the same pipeline with register-path converters for operands that TMA cannot
+// describe (unaligned pointers / strides).  B (the weights) is split and laid out as ready-to-copy
+// shared-memory images by a small prep kernel once per call.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
