@@ -41,7 +41,27 @@ def convert_to_torch_sparse(mat) -> torch.Tensor:
 
 def conv_cheb(laplacian: torch.Tensor, inputs: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     """Functional form with the reference's signature (``layers.py:113``)."""
-    return F_.cheb_conv(inputs, weight, None, F_.plan_for(laplacian))
+    return _cheb_conv_padded(inputs, weight, None, F_.plan_for(laplacian))
+
+
+def _pad4(n: int) -> int:
+    return (-n) % 4
+
+
+def _cheb_conv_padded(inputs, weight, bias, plan):
+    """Channel counts that are not multiples of 4 (21 input features, 2 outputs) would force the
+    unaligned scalar kernels (no 16-byte rows, no TMA).  Zero-padding the channel dimension of the
+    activations and of ``weight`` / ``bias`` is exact — padded inputs meet zero weights, padded outputs
+    are sliced away — and lets every layer use the vectorised / tensor-map paths; autograd slices the
+    gradients back."""
+    pin, pout = _pad4(inputs.shape[2]), _pad4(weight.shape[2])
+    if inputs.shape[2] != weight.shape[0] or (pin == 0 and pout == 0):
+        return F_.cheb_conv(inputs, weight, bias, plan)  # (a shape mismatch raises the reference's error there)
+    x = torch.nn.functional.pad(inputs, (0, pin)) if pin else inputs
+    w = torch.nn.functional.pad(weight, (0, pout, 0, 0, 0, pin)) if (pin or pout) else weight
+    b = torch.nn.functional.pad(bias, (0, pout)) if (bias is not None and pout) else bias
+    y = F_.cheb_conv(x, w, b, plan)
+    return y[..., : weight.shape[2]] if pout else y
 
 
 class ConvCheb(torch.nn.Module):
@@ -110,7 +130,7 @@ class ConvCheb(torch.nn.Module):
             if self.bias is not None:
                 out += self.bias
             return out
-        return F_.cheb_conv(inputs, self.weight, self.bias, F_.plan_for(self.laplacian))
+        return _cheb_conv_padded(inputs, self.weight, self.bias, F_.plan_for(self.laplacian))
 
 
 class NodeLinear(torch.nn.Linear):
@@ -120,7 +140,15 @@ class NodeLinear(torch.nn.Linear):
 
     def forward(self, x):
         if x.dim() == 3 and x.is_cuda and x.dtype == torch.float32:
-            return F_.NodeLinearFunction.apply(x, self.weight, self.bias)
+            pin, pout = _pad4(self.in_features), _pad4(self.out_features)
+            if x.shape[2] != self.in_features or (pin == 0 and pout == 0):
+                return F_.NodeLinearFunction.apply(x, self.weight, self.bias)
+            # zero-pad unaligned channel counts (exact; see _cheb_conv_padded)
+            xp = torch.nn.functional.pad(x, (0, pin)) if pin else x
+            w = torch.nn.functional.pad(self.weight, (0, pin, 0, pout))
+            b = torch.nn.functional.pad(self.bias, (0, pout)) if (self.bias is not None and pout) else self.bias
+            y = F_.NodeLinearFunction.apply(xp, w, b)
+            return y[..., : self.out_features] if pout else y
         return super().forward(x)
 
 
