@@ -160,6 +160,11 @@ def healpix_laplacian(nside: int, k: int = 20) -> torch.Tensor:
     return prepare_torch_laplacian(knn_laplacian(healpix_nested_xyz(nside), k))
 
 
+def equiangular_laplacian(nlat: int, nlon: int, k: int = 20) -> torch.Tensor:
+    """Rescaled k-NN Laplacian of the row-major equiangular grid (BASELINE.json cfg5: 200 x 400)."""
+    return prepare_torch_laplacian(knn_laplacian(equiangular_xyz(nlat, nlon), k))
+
+
 def nested_pool_matrices(n_fine: int, kernel: int = 4):
     """Exact pool/unpool pair for nested orderings: coarse pixel ``i`` owns fine pixels
     ``kernel*i .. kernel*i+kernel-1``.  pool rows = ``[1/kernel]*kernel``, unpool rows = ``[1]``

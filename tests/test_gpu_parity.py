@@ -491,3 +491,63 @@ def test_node_linear_matches_torch(B, V, Fin, Fout, dev, mix_mode):
     assert rel_err(xg.grad, xo.grad) < REL_TOL
     assert rel_err(lin.weight.grad, ref.weight.grad) < REL_TOL
     assert rel_err(lin.bias.grad, ref.bias.grad) < REL_TOL
+
+
+# ----------------------------------------------------------------------------------------------
+# BASELINE.json configs 4 and 5 at full node counts
+# ----------------------------------------------------------------------------------------------
+
+
+def test_cfg5_equiangular_k6_c128_matches_oracle(dev):
+    """cfg5: equiangular 400 x 200 (80 000 nodes, row-major, k-NN 20), ConvCheb K = 6, Cin = Cout = 128:
+    the irregular-degree / poor-locality stress case.  Forward, dx, dW, dbias against the oracle."""
+    from deepsphere_weather_b200 import graphs as G
+    from deepsphere_weather_b200 import layers as L
+    from oracle import cheb_oracle as O
+
+    torch.manual_seed(55)
+    lap = G.equiangular_laplacian(200, 400)
+    V, B, F, K = lap.shape[0], 2, 128, 6
+    assert V == 80000
+    x, dy = torch.randn(B, V, F), torch.randn(B, V, F)
+    w, b = torch.randn(F, K, F) * (2.0 / (F * K)) ** 0.5, torch.randn(F) * 0.1
+    xo, wo, bo = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yo = O.conv_cheb_layer(lap, xo, wo, bo)
+    yo.backward(dy)
+    layer = L.ConvCheb(F, F, K, lap).to(dev)
+    layer.set_parameters(w.to(dev), b.to(dev))
+    xg = x.to(dev).requires_grad_(True)
+    yg = layer(xg)
+    yg.backward(dy.to(dev))
+    assert rel_err(yg, yo) < REL_TOL
+    assert rel_err(xg.grad, xo.grad) < REL_TOL
+    assert rel_err(layer.weight.grad, wo.grad) < REL_TOL
+    assert rel_err(layer.bias.grad, bo.grad) < REL_TOL
+
+
+def test_cfg4_unet_nside64_shard_matches_oracle(dev):
+    """cfg4: UNetSpherical at HEALPix nside 64 (49 152 nodes), K = 4 — one per-GPU shard of the batch
+    (the path shards over samples only), forward + every parameter gradient against the CPU oracle."""
+    from deepsphere_weather_b200 import models as M
+    from oracle.unet_oracle import build_unet_oracle
+
+    V = 12 * 64 * 64
+    kw = dict(kernel_size_conv=4, pool_method="interp")
+    args = (M.default_tensor_info(V), "healpix", {"subdivisions": 64, "nest": True})
+    net = M.UNetSpherical(*args, **kw)
+    M.deterministic_fill(net, seed=4, rezero=1.0)
+    ora = build_unet_oracle(*args, laplacians=net.laplacians, **kw)
+    M.deterministic_fill(ora, seed=4, rezero=1.0)
+    torch.manual_seed(64)
+    x, yt = torch.randn(2, 3, V, 7), torch.randn(2, 1, V, 2)
+    lo = torch.nn.functional.mse_loss(ora(x), yt)
+    lo.backward()
+    net = net.to(dev)
+    yg = net(x.to(dev))
+    lg = torch.nn.functional.mse_loss(yg, yt.to(dev))
+    lg.backward()
+    assert abs(lg.item() - lo.item()) <= REL_TOL * abs(lo.item())
+    po = dict(ora.named_parameters())
+    for name, p in net.named_parameters():
+        ref = po[name].grad
+        assert rel_l2(p.grad, ref) < 2 * REL_TOL, name
