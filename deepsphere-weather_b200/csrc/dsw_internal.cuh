@@ -95,6 +95,12 @@ inline int check_launch() {
     if (_rc != DSW_OK) return _rc; \
   } while (0)
 
+// DSW_OPT_CONV_MODE -> split_pair mode (0 -> packed F2FP, 1 -> F2F per value, 2 -> integer rounding)
+inline int split_mode() {
+  const int64_t v = g_options[DSW_OPT_CONV_MODE].load(std::memory_order_relaxed);
+  return v == 1 ? 0 : v == 2 ? 2 : 1;
+}
+
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
@@ -158,3 +164,37 @@ int wgrad_pick_nsplit(int64_t N, int32_t Ka, int32_t Kb, int32_t Fin, int32_t Fo
 int launch_wgrad_simt(const WgradArgs& a, cudaStream_t st);
 
 }  // namespace dsw
+
+#ifdef __CUDACC__
+#include <cuda_bf16.h>
+namespace dsw {
+// fp32 -> (bf16 hi, bf16 lo) operand split of the tcgen05 dense kernels, two values at a time, packed
+// (first value in the low half).  hi = RN_bf16(v), lo = RN_bf16(v - hi); v - hi is exact in fp32.
+//   mode 0: one F2F.BF16.F32 per value (the slow conversion pipe: 4 per pair)
+//   mode 1: F2FP.BF16.F32.PACK_AB, one instruction per pair and image (default)
+//   mode 2: integer rounding (add half an ulp, keep the upper 16 bits): ALU / FMA pipes only
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo, int mode) {
+  if (mode == 1) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xFFFF0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - ah, b - bh);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  } else if (mode == 2) {
+    const uint32_t ua = (__float_as_uint(a) + 0x8000u) & 0xFFFF0000u, ub = (__float_as_uint(b) + 0x8000u) & 0xFFFF0000u;
+    hi = __byte_perm(ua, ub, 0x7632);
+    const float al = a - __uint_as_float(ua), bl = b - __uint_as_float(ub);
+    lo = __byte_perm(__float_as_uint(al) + 0x8000u, __float_as_uint(bl) + 0x8000u, 0x7632);
+  } else {
+    const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+    const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha)), lb = __float2bfloat16_rn(b - __bfloat162float(hb));
+    hi = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+    lo = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+  }
+}
+__device__ __forceinline__ void split_quad(const float4& v, uint2& hi, uint2& lo, int mode) {
+  split_pair(v.x, v.y, hi.x, lo.x, mode);
+  split_pair(v.z, v.w, hi.y, lo.y, mode);
+}
+}  // namespace dsw
+#endif

@@ -138,6 +138,8 @@ struct TcArgs {
   int32_t tmem_cols;     // power of two >= max(32, BN); two accumulators are allocated
   int32_t stages;        // shared-memory ring depth
   int32_t n_ctiles;      // column tiles
+  int32_t dbg;           // timing experiments only (DSW_OPT_DEBUG bits 16..256; results become wrong)
+  int32_t cmode;         // split_pair mode
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -208,6 +210,7 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tc_kernel(const __grid_consta
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int BN = P.BN;
   const int S = P.stages;
+  const int cmode = P.cmode;
   const uint32_t b_img = (uint32_t)BN * 128u;
   const uint32_t stage_bytes = 2u * A_TILE + 2u * b_img;
 
@@ -306,14 +309,11 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tc_kernel(const __grid_consta
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const uint32_t row = (t >> 4) + 16 * i;
-        __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-        split_bf16(src[i].x, h0, l0);
-        split_bf16(src[i].y, h1, l1);
-        split_bf16(src[i].z, h2, l2);
-        split_bf16(src[i].w, h3, l3);
+        uint2 qh, ql;
+        split_quad(src[i], qh, ql, cmode);
         const uint32_t off = swz(row, q >> 1) + (q & 1) * 8;
-        *reinterpret_cast<uint2*>(Ahi + off) = make_uint2(pack2(h0, h1), pack2(h2, h3));
-        *reinterpret_cast<uint2*>(Alo + off) = make_uint2(pack2(l0, l1), pack2(l2, l3));
+        *reinterpret_cast<uint2*>(Ahi + off) = qh;
+        *reinterpret_cast<uint2*>(Alo + off) = ql;
       }
     };
     const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
@@ -476,6 +476,7 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int BN = P.BN;
   const int S = P.stages;
+  const int cmode = P.cmode;
   const uint32_t b_img = (uint32_t)BN * 128u;
   const uint32_t stage_bytes = 2u * A_TILE + 2u * b_img;
 
@@ -530,6 +531,10 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
       uint8_t* Ahi = smem_gen + (size_t)s * stage_bytes;
       uint8_t* Alo = Ahi + A_TILE;
       mbar_wait(raw_full(s), ph);
+      if (P.dbg & 128) {  // timing experiment: no conversion
+        mbar_arrive(a_full(s));
+        continue;
+      }
       float4 v[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(Ahi + ((t >> 4) + 16 * i) * 256 + q * 16);
@@ -537,14 +542,11 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const uint32_t row = (t >> 4) + 16 * i;
-        __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-        split_bf16(v[i].x, h0, l0);
-        split_bf16(v[i].y, h1, l1);
-        split_bf16(v[i].z, h2, l2);
-        split_bf16(v[i].w, h3, l3);
+        uint2 qh, ql;
+        split_quad(v[i], qh, ql, cmode);
         const uint32_t off = swz(row, q >> 1) + (q & 1) * 8;
-        *reinterpret_cast<uint2*>(Ahi + off) = make_uint2(pack2(h0, h1), pack2(h2, h3));
-        *reinterpret_cast<uint2*>(Alo + off) = make_uint2(pack2(l0, l1), pack2(l2, l3));
+        *reinterpret_cast<uint2*>(Ahi + off) = qh;
+        *reinterpret_cast<uint2*>(Alo + off) = ql;
       }
       fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
       mbar_arrive(a_full(s));
@@ -563,15 +565,23 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
           if (use > 0) mbar_wait(empty(s), (use - 1) & 1);
           const int p = kbi / P.nkb, kb = kbi - p * P.nkb;
           const uint32_t st_base = smem_base + s * stage_bytes;
-          mbar_expect_tx(raw_full(s), 2u * A_TILE);
-          if (Q.rank == 2) {
-            tma_load_2d(st_base, &Q.amap[p], kb * BKB, (int)n0, raw_full(s));
+          if (P.dbg & 32) {  // timing experiment: no A transfer
+            mbar_arrive(raw_full(s));
           } else {
-            const int bb = (int)(n0 / a.rows_per_batch);
-            tma_load_3d(st_base, &Q.amap[p], kb * BKB, (int)(n0 - (int64_t)bb * a.rows_per_batch), bb, raw_full(s));
+            mbar_expect_tx(raw_full(s), 2u * A_TILE);
+            if (Q.rank == 2) {
+              tma_load_2d(st_base, &Q.amap[p], kb * BKB, (int)n0, raw_full(s));
+            } else {
+              const int bb = (int)(n0 / a.rows_per_batch);
+              tma_load_3d(st_base, &Q.amap[p], kb * BKB, (int)(n0 - (int64_t)bb * a.rows_per_batch), bb, raw_full(s));
+            }
           }
-          mbar_expect_tx(b_full(s), 2u * b_img);
-          bulk_copy_g2s(st_base + 2u * A_TILE, bsrc + (int64_t)kbi * 2 * b_img, 2u * b_img, b_full(s));
+          if (P.dbg & 64) {  // timing experiment: no B transfer
+            mbar_arrive(b_full(s));
+          } else {
+            mbar_expect_tx(b_full(s), 2u * b_img);
+            bulk_copy_g2s(st_base + 2u * A_TILE, bsrc + (int64_t)kbi * 2 * b_img, 2u * b_img, b_full(s));
+          }
         }
       }
     }
@@ -599,7 +609,7 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
           const int ksteps = (kb == P.nkb - 1) ? last_ksteps : BKB / 16;
           const uint64_t dAh = make_desc(st_base), dAl = make_desc(st_base + A_TILE);
           const uint64_t dBh = make_desc(st_base + 2u * A_TILE), dBl = make_desc(st_base + 2u * A_TILE + b_img);
-          for (int ks = 0; ks < ksteps; ++ks) {
+          for (int ks = 0; ks < ((P.dbg & 256) ? 0 : ksteps); ++ks) {
             const uint64_t adv = (uint64_t)(ks * 2);  // 32 bytes per K-step, in 16-byte units
             umma_bf16(d_tmem, dAh + adv, dBh + adv, idesc, (kbi | ks) != 0);
             umma_bf16(d_tmem, dAh + adv, dBl + adv, idesc, 1u);
@@ -627,14 +637,23 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)(buf * P.tmem_cols) + ((uint32_t)(quarter * 32) << 16);
       for (int cg = 0; cg < BN; cg += 64) {
-        const int ncol = min(64, BN - cg);  // multiple of 16
-        for (int cc = 0; cc < ncol; cc += 16) {
-          uint32_t r[16];
-          tmem_ld16(t_addr + (uint32_t)(cg + cc), r);
+        const int ncol = min(64, BN - cg);  // multiple of 16 (warp-uniform)
+        // TMEM loads two chunks (32 columns) at a time, one wait per pair
+#pragma unroll
+        for (int hq = 0; hq < 2; ++hq) {
+          if (hq * 32 >= ncol) break;
+          uint32_t r[2][16];
+          tmem_ld16(t_addr + (uint32_t)(cg + hq * 32), r[0]);
+          if (hq * 32 + 16 < ncol) tmem_ld16(t_addr + (uint32_t)(cg + hq * 32 + 16), r[1]);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<uint4*>(stg + epi_off(lane, (cc + j) >> 2)) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+          for (int q2 = 0; q2 < 2; ++q2)
+            if (hq * 32 + q2 * 16 < ncol) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<uint4*>(stg + epi_off(lane, (hq * 32 + q2 * 16 + j) >> 2)) =
+                    make_uint4(r[q2][j], r[q2][j + 1], r[q2][j + 2], r[q2][j + 3]);
+            }
         }
         __syncwarp();
         // columns of this lane in the store phase
@@ -648,23 +667,38 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
           const int cp = col / a.Cw, ccol = col - cp * a.Cw;
           const bool vec = vec_ok && (col + 3 < a.Nc) && (ccol + 3 < a.Cw);
           float* cbase = a.C + (int64_t)cp * a.sCp + ccol;
-#pragma unroll 4
-          for (int rr = 0; rr < 32; rr += 2) {
-            const int r_loc = rr + half;
-            const int64_t n = row0 + r_loc;
-            if (n >= a.N) continue;
-            float4 v = *reinterpret_cast<const float4*>(stg + epi_off(r_loc, c4));
-            v.x += bv[0], v.y += bv[1], v.z += bv[2], v.w += bv[3];
-            if (a.act == 1) v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
-            if (vec) {
-              *reinterpret_cast<float4*>(cbase + n * a.ldc) = v;
-            } else {
-              const float ve[4] = {v.x, v.y, v.z, v.w};
+          const bool relu = a.act == 1;
+          if (vec) {
+            // two phases per 16 rows so that 8 shared-memory reads, then 8 row-segment stores, overlap
+            float* cp_row = cbase + (row0 + half) * a.ldc;
+            const int64_t step = 2 * (int64_t)a.ldc;
+            int64_t n = row0 + half;
+#pragma unroll
+            for (int i0 = 0; i0 < 16; i0 += 8) {
+              float4 v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(stg + epi_off(2 * (i0 + i) + half, c4));
+#pragma unroll
+              for (int i = 0; i < 8; ++i, n += 2, cp_row += step) {
+                if (n >= a.N || (P.dbg & 16)) continue;  // dbg 16: timing experiment without the output stores
+                float4 o = v[i];
+                o.x += bv[0], o.y += bv[1], o.z += bv[2], o.w += bv[3];
+                if (relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+                *reinterpret_cast<float4*>(cp_row) = o;
+              }
+            }
+          } else {
+#pragma unroll 1
+            for (int rr = 0; rr < 32; rr += 2) {
+              const int64_t n = row0 + rr + half;
+              if (n >= a.N) continue;
+              const float4 v = *reinterpret_cast<const float4*>(stg + epi_off(rr + half, c4));
+              const float ve[4] = {v.x + bv[0], v.y + bv[1], v.z + bv[2], v.w + bv[3]};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 if (col + e >= a.Nc) break;
                 const int cpe = (col + e) / a.Cw, cce = (col + e) - cpe * a.Cw;
-                a.C[(int64_t)cpe * a.sCp + n * a.ldc + cce] = ve[e];
+                a.C[(int64_t)cpe * a.sCp + n * a.ldc + cce] = relu ? fmaxf(ve[e], 0.f) : ve[e];
               }
             }
           }
@@ -726,8 +760,14 @@ static bool encode_a_maps(const MixArgs& a, TmaArgs* Q) {
 
 }  // namespace tc
 
+// Widest column tile (DSW_OPT_MIX_BN: 0 = 256; tuning switch, multiple of 16)
+static int mix_bn_max() {
+  const int64_t v = g_options[DSW_OPT_MIX_BN].load(std::memory_order_relaxed);
+  return (v >= 16 && v <= 256 && v % 16 == 0) ? (int)v : 256;
+}
+
 size_t mix_tc_workspace_bytes(int32_t P, int32_t Ka, int32_t Nc) {
-  const int BN = std::min(256, (Nc + 15) / 16 * 16);
+  const int BN = std::min(mix_bn_max(), (Nc + 15) / 16 * 16);
   const int n_tiles = (Nc + BN - 1) / BN;
   const int nkb = (Ka + tc::BKB - 1) / tc::BKB;
   return (size_t)n_tiles * P * nkb * 2 * BN * 128 + 256;
@@ -742,8 +782,10 @@ int launch_mix_tc_ws(const MixArgs& a, void* prep, size_t prep_bytes, bool do_pr
   if (reinterpret_cast<uintptr_t>(prep) & 15) return DSW_ERR_UNSUPPORTED;
   tc::TcArgs P;
   P.m = a;
-  P.BN = std::min(256, (a.Nc + 15) / 16 * 16);
+  P.BN = std::min(mix_bn_max(), (a.Nc + 15) / 16 * 16);
   P.nkb = (a.Ka + tc::BKB - 1) / tc::BKB;
+  P.dbg = (int)g_options[DSW_OPT_DEBUG].load(std::memory_order_relaxed) & 0x1F0;
+  P.cmode = split_mode();
   int cols = 32;
   while (cols < P.BN) cols <<= 1;
   P.tmem_cols = cols;

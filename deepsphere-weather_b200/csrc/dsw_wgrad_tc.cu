@@ -118,6 +118,8 @@ struct WtcArgs {
   int32_t tmem_cols;
   int32_t kb_per_split;
   int32_t otiles;      // column tiles per Fout-side plane
+  int32_t dbg;         // timing experiments only (DSW_OPT_DEBUG bits 32..256; results become wrong)
+  int32_t cmode;       // split_pair mode
 };
 
 __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WtcArgs P) {
@@ -126,6 +128,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
   const WgradArgs& a = P.w;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int BN = P.BN, nb = P.nb;
+  const int cmode = P.cmode;
   const uint32_t a_img = 2u * BLK;            // one A image (hi or lo): two 64-channel blocks
   const uint32_t b_img = (uint32_t)nb * BLK;  // one B image
   const uint32_t stage_bytes = 2u * a_img + 2u * b_img;
@@ -251,14 +254,11 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const uint32_t row = r0 + 32 * i;
-        __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-        split_bf16(src[i].x, h0, l0);
-        split_bf16(src[i].y, h1, l1);
-        split_bf16(src[i].z, h2, l2);
-        split_bf16(src[i].w, h3, l3);
+        uint2 qh, ql;
+        split_quad(src[i], qh, ql, cmode);
         const uint32_t off = swz(row, q >> 1) + (q & 1) * 8;
-        *reinterpret_cast<uint2*>(hi_img + off) = make_uint2(pack2(h0, h1), pack2(h2, h3));
-        *reinterpret_cast<uint2*>(lo_img + off) = make_uint2(pack2(l0, l1), pack2(l2, l3));
+        *reinterpret_cast<uint2*>(hi_img + off) = qh;
+        *reinterpret_cast<uint2*>(lo_img + off) = ql;
       }
       if (do_bias && u >= 2) {
         float4& b = bsum[u - 2];
@@ -395,6 +395,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
   const WgradArgs& a = P.w;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int BN = P.BN, nb = P.nb, S = Q.stages;
+  const int cmode = P.cmode;
   const int U = 2 + nb;  // units per row block: A half 0, A half 1, B blocks
   const uint32_t stage_bytes = (uint32_t)U * UNIT;
 
@@ -449,6 +450,10 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
       const uint32_t ph = (uint32_t)(kb / S) & 1;
       uint8_t* st = smem_gen + (size_t)s * stage_bytes;
       mbar_wait(raw_full(s), ph);
+      if (P.dbg & 128) {  // timing experiment: no conversion
+        mbar_arrive(full(s));
+        continue;
+      }
       float4 v[6][4];
 #pragma unroll
       for (int u = 0; u < 6; ++u)
@@ -466,14 +471,11 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const uint32_t row = r0 + 16 * i;
-          __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-          split_bf16(v[u][i].x, h0, l0);
-          split_bf16(v[u][i].y, h1, l1);
-          split_bf16(v[u][i].z, h2, l2);
-          split_bf16(v[u][i].w, h3, l3);
+          uint2 qh, ql;
+          split_quad(v[u][i], qh, ql, cmode);
           const uint32_t off = swz(row, q >> 1) + (q & 1) * 8;
-          *reinterpret_cast<uint2*>(hi_img + off) = make_uint2(pack2(h0, h1), pack2(h2, h3));
-          *reinterpret_cast<uint2*>(lo_img + off) = make_uint2(pack2(l0, l1), pack2(l2, l3));
+          *reinterpret_cast<uint2*>(hi_img + off) = qh;
+          *reinterpret_cast<uint2*>(lo_img + off) = ql;
         }
         if (do_bias && u >= 2) {
           float4& b = bsum[u - 2];
@@ -550,16 +552,20 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
         hf[h] = half_ok[h] ? (ht - hk[h] * P.ftiles) * 64 : 0;
       }
       const CUtensorMap* ymap = &Q.maps[a.Ka + kb_plane];
-      const uint32_t tx = (uint32_t)((half_ok[1] ? 2 : 1) + nb) * UNIT;
-      for (int kb = 0; kb < nkb; ++kb) {
+            for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % S;
         const uint32_t use = (uint32_t)(kb / S);
         if (use > 0) mbar_wait(empty(s), (use - 1) & 1);
         const uint32_t st = smem_base + s * stage_bytes;
         const int64_t n0 = r_begin + (int64_t)kb * KB;
-        mbar_expect_tx(raw_full(s), tx);
+        const uint32_t tx_now = (P.dbg & 32 ? 0u : (uint32_t)(half_ok[1] ? 2 : 1) * UNIT) + (P.dbg & 64 ? 0u : (uint32_t)nb * UNIT);
+        if (tx_now == 0) {
+          mbar_arrive(raw_full(s));
+          continue;
+        }
+        mbar_expect_tx(raw_full(s), tx_now);
         for (int h = 0; h < 2; ++h) {
-          if (!half_ok[h]) continue;
+          if (!half_ok[h] || (P.dbg & 32)) continue;
           if (Q.rank == 2) {
             tma_load_2d(st + h * UNIT, &Q.maps[hk[h]], hf[h], (int)n0, raw_full(s));
           } else {
@@ -567,7 +573,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
             tma_load_3d(st + h * UNIT, &Q.maps[hk[h]], hf[h], (int)(n0 - (int64_t)bb * a.rows_per_batch), bb, raw_full(s));
           }
         }
-        for (int j = 0; j < nb; ++j) tma_load_2d(st + (2 + j) * UNIT, ymap, o_base + 64 * j, (int)n0, raw_full(s));
+        for (int j = 0; j < ((P.dbg & 64) ? 0 : nb); ++j) tma_load_2d(st + (2 + j) * UNIT, ymap, o_base + 64 * j, (int)n0, raw_full(s));
       }
     }
   } else if (lane == 0) {
@@ -582,7 +588,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
       tc_fence_after();
       const uint32_t st = smem_base + s * stage_bytes;
       const uint32_t Ah = st, Al = st + UNIT / 2, Bh = st + 2u * UNIT, Bl = Bh + UNIT / 2;
-      for (int ks = 0; ks < KB / 16; ++ks) {
+      for (int ks = 0; ks < ((P.dbg & 256) ? 0 : KB / 16); ++ks) {
         const uint32_t adv = (uint32_t)ks * 2048u;  // 16 rows = two 8-row groups
         const uint64_t dAh = make_desc_mn(Ah + adv, lbo, sbo), dAl = make_desc_mn(Al + adv, lbo, sbo);
         const uint64_t dBh = make_desc_mn(Bh + adv, lbo, sbo), dBl = make_desc_mn(Bl + adv, lbo, sbo);
@@ -675,6 +681,8 @@ int launch_wgrad_tc(const WgradArgs& a, size_t partial_bytes, cudaStream_t st) {
   int ntiles, mtiles, nsplit;
   wgrad_tc_geometry(a.N, a.Ka, a.Kb, a.Fin, a.Fout, P.BN, ntiles, mtiles, nsplit, P.kb_per_split);
   P.otiles = ntiles / a.Kb;
+  P.dbg = (int)g_options[DSW_OPT_DEBUG].load(std::memory_order_relaxed) & 0x1E0;
+  P.cmode = split_mode();
   P.w.nsplit = nsplit;
   P.nb = (P.BN + 63) / 64;
   P.ftiles = (a.Fin + 63) / 64;

@@ -273,6 +273,59 @@ class NodeLinearFunction(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------------
+# ResBlock tail: ReZero scale + residual add              reference my_models_graph.py:211-215
+# --------------------------------------------------------------------------------------------
+
+
+class RezeroResidualFunction(torch.autograd.Function):
+    """``y = rezero_weight * conv_out + skip`` in one streaming pass (``dsw_rezero_fwd``); the backward
+    produces ``rezero_weight * g`` and ``sum(g * conv_out)`` in one pass (``dsw_rezero_bwd``) and hands
+    ``g`` itself to the skip branch.  Same arithmetic as the reference's two in-place updates."""
+
+    @staticmethod
+    def forward(ctx, conv_out, skip, weight):
+        _require_cuda_f32(conv_out, "conv_out")
+        _require_cuda_f32(skip, "skip")
+        _require_cuda_f32(weight, "rezero_weight")
+        if conv_out.shape != skip.shape:
+            raise ValueError(f"residual shapes differ: {tuple(conv_out.shape)} vs {tuple(skip.shape)}")
+        if weight.numel() != 1:
+            raise ValueError("rezero_weight must hold one element")
+        a = conv_out.contiguous()
+        s = skip.contiguous()
+        y = torch.empty_like(a)
+        with torch.cuda.device(a.device):
+            rc = _lib.load().dsw_rezero_fwd(a.data_ptr(), s.data_ptr(), weight.data_ptr(), y.data_ptr(), a.numel(),
+                                            _stream_ptr(a.device))
+        _lib.check(rc, "dsw_rezero_fwd")
+        ctx.save_for_backward(a, weight)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        a, weight = ctx.saved_tensors
+        lib = _lib.load()
+        g = g.contiguous()
+        need_a, need_s, need_w = ctx.needs_input_grad
+        da = torch.empty_like(a) if need_a else None
+        dw = torch.empty_like(weight) if need_w else None
+        if need_a or need_w:
+            with torch.cuda.device(a.device):
+                ws = _workspace(lib.dsw_rezero_bwd_workspace_bytes(), a.device)
+                rc = lib.dsw_rezero_bwd(g.data_ptr(), a.data_ptr(), weight.data_ptr(),
+                                        da.data_ptr() if da is not None else None,
+                                        dw.data_ptr() if dw is not None else None, ws.data_ptr(), ws.numel(), a.numel(),
+                                        _stream_ptr(a.device))
+            _lib.check(rc, "dsw_rezero_bwd")
+        return da, (g if need_s else None), dw
+
+
+def rezero_residual(conv_out, skip, weight):
+    return RezeroResidualFunction.apply(conv_out, skip, weight)
+
+
+# --------------------------------------------------------------------------------------------
 # Sparse remap                                                     reference layers.py:956-964
 # --------------------------------------------------------------------------------------------
 

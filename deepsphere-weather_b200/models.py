@@ -24,6 +24,7 @@ from . import graphs as G
 
 
 def _default_backend():
+    from . import functional as F_
     from . import layers as L
 
     return SimpleNamespace(
@@ -31,6 +32,7 @@ def _default_backend():
         Linear=L.NodeLinear,
         healpix_pools={"max": (L.HealpixMaxPool, L.HealpixMaxUnpool), "avg": (L.HealpixAvgPool, L.HealpixAvgUnpool)},
         general_pools=L.PoolUnpoolBlock.getGeneralPoolUnpoolLayer,
+        rezero_residual=F_.rezero_residual,
     )
 
 
@@ -95,6 +97,9 @@ class ResBlock(torch.nn.Module):
             self.res_connection = getattr(backend, "Linear", torch.nn.Linear)(in_channels, widths[-1])
         if self.rezero:
             self.rezero_weight = torch.nn.Parameter(torch.zeros(1), requires_grad=True)
+        # fused `out * rezero_weight + skip` of the backend, if it has one
+        backend = convblock_kwargs.get("backend") or _default_backend()
+        self._fused_tail = getattr(backend, "rezero_residual", None)
         if convblock_kwargs.get("batch_norm", False):
             last = getattr(self, self.conv_names_list[-1])
             torch.nn.init.constant_(last.bn.weight, 0)
@@ -104,6 +109,8 @@ class ResBlock(torch.nn.Module):
         out = x
         for name in self.conv_names_list:
             out = getattr(self, name)(out)
+        if self.rezero and self._fused_tail is not None:
+            return self._fused_tail(out, self.res_connection(x), self.rezero_weight)
         if self.rezero:
             out *= self.rezero_weight
         out += self.res_connection(x)

@@ -195,6 +195,18 @@ int dsw_nested_sum(const float* x, int64_t x_sB, int64_t x_sV, float* y, int32_t
                    int32_t F, int32_t kernel, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * ResBlock tail: y = w * conv_out + skip  (ReZero scale + residual add), n = B*V*F elements, w a
+ * device scalar.  Replaces `x_out *= self.rezero_weight; x_out += self.res_connection(x)`
+ * (reference modules/my_models_graph.py:211-215) and the passes autograd derives from them.
+ * bwd: d_conv_out = w * g (nullable), d_w = sum(g * conv_out) (nullable; needs conv_out and the
+ * workspace; fixed-order reduction); the gradient of `skip` is g itself.
+ * ------------------------------------------------------------------------------------------- */
+int dsw_rezero_fwd(const float* conv_out, const float* skip, const float* w, float* y, int64_t n, void* stream);
+size_t dsw_rezero_bwd_workspace_bytes(void);
+int dsw_rezero_bwd(const float* g, const float* conv_out, const float* w, float* d_conv_out, float* d_w, void* workspace,
+                   size_t workspace_bytes, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Introspection used by bench.py / tests.
  * ------------------------------------------------------------------------------------------- */
 /* Number of kernels launched by this library since process start (all threads). */
@@ -206,11 +218,15 @@ int dsw_get_mix_mode(void);
 enum {
   DSW_OPT_HOP_KERNEL = 0,    /* 0 = auto (bulk-copy-staged tile kernel), 1 = row-block kernel through L1, 2 = plain CSR, 3 = panel-staged L1 tile kernel */
   DSW_OPT_L2_CHUNK_BYTES = 1, /* working-set budget (bytes) of L2-resident sample chunks; 0 / 1 = chunking off (default) */
-  DSW_OPT_DEBUG = 2,          /* timing experiments only (results become wrong): 1 = hops skip staging, 2 = hops skip the FMA loop */
+  DSW_OPT_DEBUG = 2,          /* timing experiments only (results become wrong): 1 = hops skip staging, 2 = hops skip the FMA loop;
+                                 dense kernels, bit mask: 16 = no output stores, 32 = no A transfers, 64 = no B transfers,
+                                 128 = no bf16 conversion, 256 = no MMAs */
   DSW_OPT_NO_TMA = 3,         /* 1 = stage tiles with cp.async / register loads instead of tensor-map TMA */
   DSW_OPT_FWD_ALGO = 4,       /* 0 = auto by channel counts, 1 = TERMS (hops on Fin, then mix), 2 = CLENSHAW (mix, then hops on Fout) */
   DSW_OPT_BWD_ALGO = 5,       /* 0 = auto, 1 = TERMS (hops on dy, Fout channels), 2 = CLENSHAW (hops on Fin channels) */
-  DSW_OPT_COUNT = 6
+  DSW_OPT_MIX_BN = 6,         /* widest column tile of the tcgen05 channel mix (0 = 256; multiple of 16) */
+  DSW_OPT_CONV_MODE = 7,      /* fp32 -> bf16 hi/lo split of the dense kernels: 0 = packed F2FP (default), 1 = one F2F per value, 2 = integer rounding */
+  DSW_OPT_COUNT = 8
 };
 /* Tuning only: with DSW_OPT_DEBUG = 4 the hop kernel sums per-phase SM cycles over its teams
  * (issue staging, wait for tile + Z/G, entry loop, stores, item count). */

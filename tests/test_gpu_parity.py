@@ -498,6 +498,37 @@ def test_node_linear_matches_torch(B, V, Fin, Fout, dev, mix_mode):
 # ----------------------------------------------------------------------------------------------
 
 
+@pytest.mark.parametrize("shape", [(2, 768, 64), (3, 130, 7), (1, 5, 2), (4, 3072, 128)])
+@pytest.mark.parametrize("w0", [0.0, 0.7])
+def test_rezero_residual_matches_torch(shape, w0, dev):
+    """Fused ResBlock tail y = w * conv_out + skip against the reference's two in-place updates
+    (my_models_graph.py:211-215) evaluated by torch on the CPU; w = 0 is the ReZero initial value."""
+    from deepsphere_weather_b200 import functional as F_
+
+    torch.manual_seed(3)
+    a, s, g = torch.randn(*shape), torch.randn(*shape), torch.randn(*shape)
+    w = torch.full((1,), w0)
+    ar, sr, wr = a.clone().requires_grad_(True), s.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    out = ar * 1.0
+    out *= wr
+    out += sr
+    out.backward(g)
+    ad, sd, wd = (t.to(dev).requires_grad_(True) for t in (a, s, w))
+    y = F_.rezero_residual(ad, sd, wd)
+    y.backward(g.to(dev))
+    assert torch.equal(y.detach().cpu(), (a * w + s)) or rel_err(y, out.detach().numpy()) < 1e-6
+    assert rel_err(sd.grad, sr.grad.numpy()) == 0.0
+    if w0 != 0.0:
+        assert rel_err(ad.grad, ar.grad.numpy()) < 1e-6
+    else:
+        assert float(ad.grad.abs().max()) == 0.0
+    assert abs(float(wd.grad) - float(wr.grad)) <= 2e-5 * max(1.0, abs(float(wr.grad)))
+    # strided inputs (a sliced padded conv output) are accepted
+    wide = torch.randn(shape[0], shape[1], shape[2] + 2, device=dev)
+    y2 = F_.rezero_residual(wide[..., : shape[2]], sd.detach(), wd.detach())
+    assert rel_err(y2, (wide[..., : shape[2]].cpu() * w + s).numpy()) < 1e-6
+
+
 def test_cfg5_equiangular_k6_c128_matches_oracle(dev):
     """cfg5: equiangular 400 x 200 (80 000 nodes, row-major, k-NN 20), ConvCheb K = 6, Cin = Cout = 128:
     the irregular-degree / poor-locality stress case.  Forward, dx, dW, dbias against the oracle."""
