@@ -9,6 +9,7 @@
 #include "dsw.h"
 
 #define DSW_TILE_BLOCKS 32
+#define HOP_CNT_SLOTS 64
 
 struct dsw_csr {
   int32_t n_rows = 0, n_cols = 0;
@@ -50,6 +51,10 @@ struct dsw_rb {
   int32_t* tp_ptr = nullptr;     // [n_tiles + 1] cumulative entry steps
   float4* tp_val = nullptr;      // [total_steps][32] R = 4 weights
   uint32_t* tp_off = nullptr;    // [total_steps][32] byte offset of the source row inside the staged tile (256 B rows)
+  // Dynamic item scheduling of the tile hop kernel: HOP_CNT_SLOTS rotating sets of per-tile claim
+  // counters (all zero between uses) and the host-side launch counter that picks the set.
+  int32_t* hop_cnt = nullptr;               // [HOP_CNT_SLOTS][n_tiles]
+  std::atomic<uint32_t>* hop_ring = nullptr;
   int32_t* blkptr = nullptr;   // [n_blocks + 1] offsets into ucol / uval panels
   int32_t* ucol = nullptr;     // [total_union]
   float* uval = nullptr;       // [total_union * R]  (entry u, row r) at uval[u*R + r]

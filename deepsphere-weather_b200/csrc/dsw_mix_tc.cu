@@ -498,13 +498,13 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
   if (t == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(raw_full(s), 1);
-      mbar_init(a_full(s), N_CONV_WARPS * 32);
+      mbar_init(a_full(s), N_CONV_WARPS);  // one elected arrival per converter warp
       mbar_init(b_full(s), 1);
       mbar_init(empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(acc_full(b), 1);
-      mbar_init(acc_empty(b), 128);
+      mbar_init(acc_empty(b), 4);  // one elected arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
       uint8_t* Alo = Ahi + A_TILE;
       mbar_wait(raw_full(s), ph);
       if (P.dbg & 128) {  // timing experiment: no conversion
-        mbar_arrive(a_full(s));
+        if (lane == 0) mbar_arrive(a_full(s));
         continue;
       }
       float4 v[8];
@@ -549,7 +549,8 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
         *reinterpret_cast<uint2*>(Alo + off) = ql;
       }
       fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
-      mbar_arrive(a_full(s));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full(s));
     }
   } else if (warp == WARP_BLOAD) {
     // ================= producer (one thread): TMA of the raw A block + bulk copy of the B images =================
@@ -706,7 +707,8 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
         __syncwarp();
       }
       tc_fence_before();
-      mbar_arrive(acc_empty(buf));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(buf));
     }
   }
   tc_fence_before();

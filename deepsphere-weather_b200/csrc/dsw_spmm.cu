@@ -323,6 +323,8 @@ struct TeamHopPlan {
   int32_t n_items;        // B * n_slabs
   int32_t items_per_cta;
   int32_t n_teams;
+  int32_t* cnt;           // per-tile claim counters of this launch (dynamic item scheduling) or null
+  int32_t* cnt_clear;     // counter slot this launch zeroes for a later launch
   int32_t debug_skip;     // timing experiments only: 1 = skip staging, 2 = skip the entry loop
 };
 
@@ -389,61 +391,45 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1)
   // TMA variant: s_row holds the pieces (first source row), s_meta their (local row, log2 length)
   uint32_t* s_meta = reinterpret_cast<uint32_t*>(s_row + ((P.cap_rows + 1) & ~1));
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_meta + ((P.cap_pieces + 1) & ~1));
+  int32_t* s_claim = reinterpret_cast<int32_t*>(s_bar + MAX_TEAMS);  // [team][2] next claimed item; [2 * MAX_TEAMS] = exit flag
   const int pc0 = TMA ? __ldg(P.tpc_ptr + tile) : 0;
   const int npieces = TMA ? __ldg(P.tpc_ptr + tile + 1) - pc0 : 0;
 
-  {
-    const float4* gv = P.tp_val + (size_t)t0 * DSW_TILE_BLOCKS;
-    const uint32_t* go = P.tp_off + (size_t)t0 * DSW_TILE_BLOCKS;
-    const int n_real = len * DSW_TILE_BLOCKS, n_all = (len + PANEL_PAD) * DSW_TILE_BLOCKS;
-    for (int i = tid; i < n_all; i += blockDim.x) {
-      s_val[i] = i < n_real ? __ldg(gv + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-      s_off[i] = i < n_real ? __ldg(go + i) : 0u;
+  // Dynamic scheduling: the CTAs of one tile (blockIdx.y = 0 .. gridDim.y - 1) claim its work items
+  // from a global counter, so late CTAs share what is left and CTAs that find nothing leave at once.
+  int32_t* cnt = P.cnt ? P.cnt + tile : nullptr;
+  if (cnt) {
+    if (tid == 0) {
+      if (P.cnt_clear && blockIdx.y == 0) P.cnt_clear[tile] = 0;
+      s_claim[2 * MAX_TEAMS] = atomicAdd(cnt, 0) >= P.n_items;
     }
-    if (TMA) {
-      for (int i = tid; i < npieces; i += blockDim.x) {
-        s_row[i] = __ldg(P.tpc_row + pc0 + i);
-        s_meta[i] = __ldg(P.tpc_meta + pc0 + i);
-      }
-      if (tid < MAX_TEAMS) hop_mbar_init(hop_smem_u32(s_bar + tid), 1);
-      if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    } else {
-      for (int i = tid; i < nrows; i += blockDim.x) s_row[i] = __ldg(P.tile_row + r0 + i);
+    __syncthreads();
+    if (s_claim[2 * MAX_TEAMS]) return;
+  }
+
+  // ---- prologue, part 1: the source-row list (TMA: piece list + mbarriers) ----
+  if (TMA) {
+    for (int i = tid; i < npieces; i += blockDim.x) {
+      s_row[i] = __ldg(P.tpc_row + pc0 + i);
+      s_meta[i] = __ldg(P.tpc_meta + pc0 + i);
     }
+    if (tid < MAX_TEAMS) hop_mbar_init(hop_smem_u32(s_bar + tid), 1);
+    if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else {
+    for (int i = tid; i < nrows; i += blockDim.x) s_row[i] = __ldg(P.tile_row + r0 + i);
   }
   __syncthreads();
 
   const int team = tid / TEAM_THREADS;
-  if (team >= P.n_teams) return;
   const int tt = tid - team * TEAM_THREADS;
-  const int slot = tt >> 2, l4 = tt & 3, par = slot & 1;
-  const int blk = blk0 + slot;
-  const bool active = blk < P.n_blocks;
-  int my_len = 0;
-  if (active) my_len = __ldg(P.blkptr + blk + 1) - __ldg(P.blkptr + blk);
-  // uniform trip count of the warp (8 row-blocks), rounded up to the 2-step pipeline
-  const int wlen = (__reduce_max_sync(0xffffffffu, my_len) + 1) & ~1;
-
-  uint8_t* xs = tile_smem + (size_t)team * xbuf_bytes;
+  uint8_t* xs = tile_smem + (size_t)(team < P.n_teams ? team : 0) * xbuf_bytes;
   const uint32_t xs_u32 = (uint32_t)__cvta_generic_to_shared(xs);
-  // byte offsets of this lane's float4 columns inside a staged row: j = 0/2 through cA, j = 1/3 through cB
-  const uint32_t cA = (uint32_t)(l4 * 16) ^ (uint32_t)(par * 64);
-  const uint32_t cB = (uint32_t)(l4 * 16 + 64) ^ (uint32_t)(par * 64);
-  const uint8_t* xA = xs + cA;
-  const uint8_t* xB = xs + cB;
-  const uint32_t* po = s_off + slot;
-  const float4* pw = s_val + slot;
-  // channel of accumulator column j inside the slab
-  int ch[4];
-  ch[0] = (int)(cA >> 2), ch[1] = (int)(cB >> 2), ch[2] = ch[0] + 32, ch[3] = ch[1] + 32;
-
-  uint32_t phase = 0;
-  const int item_begin = blockIdx.y * P.items_per_cta;
-  const int item_end = min(item_begin + P.items_per_cta, P.n_items);
+  const int item_begin = cnt ? 0 : blockIdx.y * P.items_per_cta;
+  const int item_end = cnt ? P.n_items : min(item_begin + P.items_per_cta, P.n_items);
   // Stages the source rows of one item into the team's buffer.  TMA: issued by the lanes of the team's
-  // first warp; called for the first item before the loop and for the next item as soon as the entry
-  // loop of the current one is done (the buffer is free then), so that the transfer overlaps the
-  // output stores and the next item's Z / G loads.
+  // first warp; called for the first item right here (the transfer overlaps the panel staging below) and
+  // for the next item as soon as the entry loop of the current one is done (the buffer is free then), so
+  // that the transfer overlaps the output stores and the next item's Z / G loads.
   auto stage = [&](int item) {
     const int b = item / P.n_slabs, slab = item - b * P.n_slabs;
     const int slab_f = min(64, a.F - slab * 64);
@@ -480,9 +466,53 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1)
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
   };
-  if (TMA && item_begin + team < item_end) stage(item_begin + team);
+  // first item of the team: claimed (dynamic) or item_begin + team (static)
+  int item = item_begin + team;
+  if (cnt && team < P.n_teams) {
+    if (tt == 0) s_claim[2 * team] = atomicAdd(cnt, 1);
+    team_sync(team);
+    item = s_claim[2 * team];
+  }
+  if (TMA && team < P.n_teams && item < item_end) stage(item);
 
-  for (int item = item_begin + team; item < item_end; item += P.n_teams) {
+  // ---- prologue, part 2: the entry-major weight / offset panels ----
+  {
+    const float4* gv = P.tp_val + (size_t)t0 * DSW_TILE_BLOCKS;
+    const uint32_t* go = P.tp_off + (size_t)t0 * DSW_TILE_BLOCKS;
+    const int n_real = len * DSW_TILE_BLOCKS, n_all = (len + PANEL_PAD) * DSW_TILE_BLOCKS;
+    for (int i = tid; i < n_all; i += blockDim.x) {
+      s_val[i] = i < n_real ? __ldg(gv + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s_off[i] = i < n_real ? __ldg(go + i) : 0u;
+    }
+  }
+  __syncthreads();
+
+  if (team >= P.n_teams) return;
+  const int slot = tt >> 2, l4 = tt & 3, par = slot & 1;
+  const int blk = blk0 + slot;
+  const bool active = blk < P.n_blocks;
+  int my_len = 0;
+  if (active) my_len = __ldg(P.blkptr + blk + 1) - __ldg(P.blkptr + blk);
+  // uniform trip count of the warp (8 row-blocks), rounded up to the 2-step pipeline
+  const int wlen = (__reduce_max_sync(0xffffffffu, my_len) + 1) & ~1;
+
+  // byte offsets of this lane's float4 columns inside a staged row: j = 0/2 through cA, j = 1/3 through cB
+  const uint32_t cA = (uint32_t)(l4 * 16) ^ (uint32_t)(par * 64);
+  const uint32_t cB = (uint32_t)(l4 * 16 + 64) ^ (uint32_t)(par * 64);
+  const uint8_t* xA = xs + cA;
+  const uint8_t* xB = xs + cB;
+  const uint32_t* po = s_off + slot;
+  const float4* pw = s_val + slot;
+  // channel of accumulator column j inside the slab
+  int ch[4];
+  ch[0] = (int)(cA >> 2), ch[1] = (int)(cB >> 2), ch[2] = ch[0] + 32, ch[3] = ch[1] + 32;
+
+  uint32_t phase = 0;
+  int claim_par = 1;  // slot parity of the claim made during this item (slot 0 held the first one)
+  while (item < item_end) {
+    // claim the next item now; the index is read after the entry loop, when the round trip is long over
+    if (cnt && tt == 0) s_claim[2 * team + claim_par] = atomicAdd(cnt, 1);
+    int next_item = item_end;
     const int b = item / P.n_slabs, slab = item - b * P.n_slabs;
     const int slab_f = min(64, a.F - slab * 64);       // channels in this slab (multiple of 4)
     const int cpr = slab_f >> 2;                        // 16-byte chunks per row
@@ -577,7 +607,8 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1)
     if (TMA) {
       // every lane of the team is done reading the staged rows: the next item's transfer may start
       team_sync(team);
-      if (item + P.n_teams < item_end) stage(item + P.n_teams);
+      next_item = cnt ? s_claim[2 * team + claim_par] : item + P.n_teams;
+      if (next_item < item_end) stage(next_item);
     }
     if (prof) t3 = clock64();
     // ---- epilogue: O = alpha * acc ----
@@ -596,7 +627,10 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1)
       }
     }
     // every lane of the team is done reading the staged rows before the next item overwrites them
-    if (!TMA) team_sync(team);
+    if (!TMA) {
+      team_sync(team);
+      next_item = cnt ? s_claim[2 * team + claim_par] : item + P.n_teams;
+    }
     if (prof) {
       const long long t4 = clock64();
       atomicAdd(&g_hop_prof[0], (unsigned long long)(t1 - t0));  // issue staging
@@ -605,6 +639,8 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1)
       atomicAdd(&g_hop_prof[3], (unsigned long long)(t4 - t3));  // stores + team barrier
       atomicAdd(&g_hop_prof[4], 1ull);                           // items
     }
+    item = next_item;
+    claim_par ^= 1;
   }
 }
 
@@ -625,7 +661,11 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
   const int hop_mode = (int)g_options[DSW_OPT_HOP_KERNEL].load(std::memory_order_relaxed);
   // 32-bit byte offsets inside one sample: (n_cols - 1) * x_sV * 4 + F * 4 must fit
   const bool off32 = ((int64_t)A.n_cols * a.x_sV + a.F) * 4 < ((int64_t)1 << 32);
-  if (v4 && rb.R == 4 && hop_mode == 0 && rb.n_tiles > 0) {
+  // narrow planes (the 64 -> 2 output layer runs its hops on 4 channels): a 64-channel slab would be
+  // mostly padding, the plain CSR kernel moves only the real channels
+  const int64_t small_f_opt = g_options[DSW_OPT_HOP_SMALL_F].load(std::memory_order_relaxed);
+  const int small_f = small_f_opt > 0 ? (int)small_f_opt : 8;
+  if (v4 && rb.R == 4 && hop_mode == 0 && rb.n_tiles > 0 && a.F > small_f) {
     const size_t panels = (size_t)(rb.tile_len_max + PANEL_PAD) * DSW_TILE_BLOCKS * 20 + (size_t)((rb.tile_rows_max + 1) & ~1) * 4 +
                           (size_t)((rb.tile_pieces_max + 1) & ~1) * 4 + 8 * MAX_TEAMS + 64;
     const size_t xbuf = (size_t)rb.tile_rows_max * 256;
@@ -646,9 +686,24 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
       int ipc = n_teams;
       while (ipc < 4 * n_teams && ipc * 2 <= P.n_items && (int64_t)rb.n_tiles * ceil_div(P.n_items, ipc * 2) >= 148 * 3)
         ipc *= 2;
+      {  // tuning override: items per CTA (rounded up to a multiple of the team count)
+        const int64_t o = g_options[DSW_OPT_HOP_IPC].load(std::memory_order_relaxed);
+        if (o > 0) ipc = std::min<int>((int)((o + n_teams - 1) / n_teams * n_teams), std::max(P.n_items, n_teams));
+      }
       P.items_per_cta = ipc;
       const size_t smem = (size_t)n_teams * xbuf + panels;
       dim3 grid(rb.n_tiles, ceil_div(P.n_items, ipc));
+      // Dynamic scheduling (default): the CTAs of a tile claim items from a per-tile counter.  One CTA
+      // per tile plus enough extra rows of CTAs to fill the machine and to share the tiles of the last,
+      // partial round; CTAs that find their tile finished leave before staging anything.  Counter slots
+      // rotate per launch: this launch zeroes the slot that will be used HOP_CNT_SLOTS / 2 launches later.
+      if (rb.hop_cnt && rb.hop_ring && g_options[DSW_OPT_HOP_IPC].load(std::memory_order_relaxed) == 0) {
+        const uint32_t k = rb.hop_ring->fetch_add(1, std::memory_order_relaxed);
+        P.cnt = rb.hop_cnt + (size_t)(k % HOP_CNT_SLOTS) * rb.n_tiles;
+        P.cnt_clear = rb.hop_cnt + (size_t)((k + HOP_CNT_SLOTS / 2) % HOP_CNT_SLOTS) * rb.n_tiles;
+        const int rows = std::min(ceil_div(P.n_items, n_teams), ceil_div(148, rb.n_tiles) + 1);
+        grid = dim3(rb.n_tiles, std::max(rows, 1));
+      }
       // tensor maps of the gather source [B][n_cols][F] with boxes of 1 .. 128 rows x 64 channels
       HopMaps maps;
       bool tma = g_options[DSW_OPT_NO_TMA].load(std::memory_order_relaxed) == 0 && rb.tile_pieces_max > 0 &&
@@ -699,7 +754,7 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
       return check_launch();
     }
   }
-  if (v4 && rb.R > 0 && hop_mode <= 1) {
+  if (v4 && rb.R > 0 && hop_mode <= 1 && a.F > small_f) {
     const int threads = 512;
     const int slots = threads / 16;
     dim3 grid(ceil_div(rb.n_blocks, slots), ceil_div(a.F, 64), a.B);

@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
   if (t == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(raw_full(s), 1);
-      mbar_init(full(s), T_CONV);
+      mbar_init(full(s), T_CONV / 32);  // one elected arrival per converter warp
       mbar_init(empty(s), 1);
     }
     fence_mbar_init();
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
       uint8_t* st = smem_gen + (size_t)s * stage_bytes;
       mbar_wait(raw_full(s), ph);
       if (P.dbg & 128) {  // timing experiment: no conversion
-        mbar_arrive(full(s));
+        if (lane == 0) mbar_arrive(full(s));
         continue;
       }
       float4 v[6][4];
@@ -484,7 +484,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
         }
       }
       fence_proxy_async();
-      mbar_arrive(full(s));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full(s));
     }
 
     // ---- dbias partial (fp32, CTA-local reduction through shared memory) ----
