@@ -8,7 +8,7 @@
 
 #include "dsw.h"
 
-#define DSW_TILE_BLOCKS 32
+#define DSW_TILE_BLOCKS 16
 #define HOP_CNT_SLOTS 64
 
 struct dsw_csr {

@@ -216,17 +216,37 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradArgs a, int32_t ft
   }
 }
 
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int32_t nsplit, int64_t n_w,
-                                    int32_t Fout, float* __restrict__ dW, float* __restrict__ dbias) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// Sum of the split partials in a fixed order (deterministic).  A CTA owns 32 consecutive outputs; its 8
+// warps each add every 8th partial (coalesced 128-byte reads, independent loads in flight), then warp 0
+// adds the 8 warp sums in warp order.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int32_t nsplit, int64_t n_w,
+                                                           int32_t Fout, float* __restrict__ dW, float* __restrict__ dbias) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t total = n_w + Fout;
-  if (i >= total) return;
+  const int64_t i = (int64_t)blockIdx.x * 32 + lane;
   float s = 0.f;
-  for (int sp = 0; sp < nsplit; ++sp) s += __ldg(partial + (int64_t)sp * total + i);
-  if (i < n_w)
-    dW[i] = s;
-  else if (dbias)
-    dbias[i - n_w] = s;
+  if (i < total) {
+    const float* p = partial + i;
+    int sp = w;
+    for (; sp + 24 < nsplit; sp += 32) {
+      const float v0 = __ldg(p + (int64_t)sp * total), v1 = __ldg(p + (int64_t)(sp + 8) * total);
+      const float v2 = __ldg(p + (int64_t)(sp + 16) * total), v3 = __ldg(p + (int64_t)(sp + 24) * total);
+      s += v0, s += v1, s += v2, s += v3;
+    }
+    for (; sp < nsplit; sp += 8) s += __ldg(p + (int64_t)sp * total);
+  }
+  red[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && i < total) {
+    float t = red[0][lane];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) t += red[j][lane];
+    if (i < n_w)
+      dW[i] = t;
+    else if (dbias)
+      dbias[i - n_w] = t;
+  }
 }
 
 int wgrad_pick_nsplit(int64_t N, int32_t Ka, int32_t Kb, int32_t Fin, int32_t Fout) {
@@ -240,7 +260,7 @@ int launch_wgrad_reduce(const float* partial, int32_t nsplit, int32_t K, int32_t
                         float* dbias, cudaStream_t st) {
   const int64_t n_w = (int64_t)K * Fin * Fout;
   const int64_t total = n_w + Fout;
-  wgrad_reduce_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(partial, nsplit, n_w, Fout, dW, dbias);
+  wgrad_reduce_kernel<<<(unsigned)ceil_div64(total, 32), 256, 0, st>>>(partial, nsplit, n_w, Fout, dW, dbias);
   return check_launch();
 }
 

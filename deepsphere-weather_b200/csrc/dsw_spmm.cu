@@ -303,8 +303,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) hop_tile_kernel(const int32_t
 // row-blocks that share a quarter-warp phase read opposite 64-byte halves of their rows (column
 // group XOR parity), which keeps the 128-bit reads bank-conflict free.
 // ---------------------------------------------------------------------------------------------
-constexpr int TEAM_THREADS = 128;   // 32 row-blocks x 4 lanes
-constexpr int MAX_TEAMS = 3;
+constexpr int TEAM_THREADS = DSW_TILE_BLOCKS * 4;   // 4 lanes per row-block
+constexpr int MAX_TEAMS = 5;
 constexpr int PANEL_PAD = 4;        // zero entry steps appended so that the pipeline may over-read
 
 struct TeamHopPlan {
@@ -701,7 +701,8 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
         const uint32_t k = rb.hop_ring->fetch_add(1, std::memory_order_relaxed);
         P.cnt = rb.hop_cnt + (size_t)(k % HOP_CNT_SLOTS) * rb.n_tiles;
         P.cnt_clear = rb.hop_cnt + (size_t)((k + HOP_CNT_SLOTS / 2) % HOP_CNT_SLOTS) * rb.n_tiles;
-        const int rows = std::min(ceil_div(P.n_items, n_teams), ceil_div(148, rb.n_tiles) + 1);
+        const int64_t extra = g_options[DSW_OPT_HOP_ROWS].load(std::memory_order_relaxed);
+        const int rows = std::min(ceil_div(P.n_items, n_teams), ceil_div(148, rb.n_tiles) + (extra > 0 ? (int)extra : 3));
         grid = dim3(rb.n_tiles, std::max(rows, 1));
       }
       // tensor maps of the gather source [B][n_cols][F] with boxes of 1 .. 128 rows x 64 channels

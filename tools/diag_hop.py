@@ -15,7 +15,7 @@ from deepsphere_weather_b200 import _lib  # noqa: E402
 from deepsphere_weather_b200 import functional as F_  # noqa: E402
 from deepsphere_weather_b200 import graphs as G  # noqa: E402
 
-OPT_DEBUG, OPT_IPC, OPT_SMALL_F = 2, 8, 9
+OPT_DEBUG, OPT_IPC, OPT_SMALL_F, OPT_ROWS = 2, 8, 9, 10
 
 
 def timed(fn, flush, iters=8, warm=3):
@@ -45,11 +45,15 @@ def main():
         x = torch.randn(B, V, F, device=dev)
         K = 4
         row = []
-        for ipc in [0, 3, 6, 12, 24, 33, 48, 96]:
+        for ipc in [0, 12, 24]:
             lib.dsw_set_option(OPT_IPC, ipc)
             row.append((ipc, timed(lambda: F_.cheb_terms(x, plan, K), flush)))
         lib.dsw_set_option(OPT_IPC, 0)
         extra = ""
+        for rows in (1, 2, 3, 5, 8):
+            lib.dsw_set_option(OPT_ROWS, rows)
+            extra += f"  rows+{rows}={timed(lambda: F_.cheb_terms(x, plan, K), flush):7.1f}"
+        lib.dsw_set_option(OPT_ROWS, 0)
         if F <= 24:
             lib.dsw_set_option(OPT_SMALL_F, 32)
             extra = f"  csr-path {timed(lambda: F_.cheb_terms(x, plan, K), flush):7.1f}"
