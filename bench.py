@@ -198,10 +198,10 @@ def time_kernel_rooflines(device, hbm_gbs, bf16_tflops):
     per_launch_bytes = alg_bytes / n_launch
     achieved = alg_bytes / t / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the three hop launches in
-    # profiles/r01h_hop_team_kernel_ncu.txt (one `ncu --set full` capture of this same call):
-    # (458.4 + 363.2) + (868.3 + 373.9) + (868.5 + 374.1) MB over 3 launches.  Each unfused hop moves
+    # profiles/r01j_hop_team_kernel_ncu.txt (one `ncu --set full` capture of this same call):
+    # (463.2 + 361.0) + (867.4 + 373.5) + (867.2 + 374.4) MB over 3 launches.  Each unfused hop moves
     # ~3 planes (gather source, k-2 term, output) where the K-plane accounting counts 4/3.
-    ncu_traffic_bytes_per_launch = 1102.1e6
+    ncu_traffic_bytes_per_launch = 1102.2e6
     out["roofline"] = {
         "kernel": "hop_team_kernel (Chebyshev SpMM hop), dsw_cheb_terms nside64 B32 F64 K4", "bound": "hbm",
         "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
@@ -209,6 +209,35 @@ def time_kernel_rooflines(device, hbm_gbs, bf16_tflops):
         "launches": n_launch, "us_per_launch": t / n_launch * 1e6, "algorithmic_bytes_per_launch": per_launch_bytes,
     }
     del x, lap
+
+    # --- cfg2: one ConvCheb layer, nside 32, B 32, 64 -> 64, K 4 (BASELINE.json configs[1]) ---
+    from deepsphere_weather_b200 import layers as L_
+
+    nside, B, F, K = 32, 32, 64, 4
+    lap = G.healpix_laplacian(nside)
+    layer = L_.ConvCheb(F, F, K, lap).to(device)
+    V = lap.shape[0]
+    x = torch.randn(B, V, F, device=device)
+    with torch.no_grad():
+        t_fwd = timed(lambda: layer(x))
+    xg = x.clone().requires_grad_(True)
+    dy = torch.randn(B, V, F, device=device)
+
+    def fwd_bwd():
+        layer.zero_grad(set_to_none=True)
+        xg.grad = None
+        layer(xg).backward(dy)
+
+    t_fb = timed(fwd_bwd)
+    nnz_bytes = F_.plan_for(layer.laplacian).operand_bytes
+    fused_bytes = 4 * B * V * F * 2 + nnz_bytes + 4 * K * F * F + 4 * F      # fused-layer compulsory traffic
+    flops = 2 * (nnz_bytes // 8) * F * B * (K - 1) + 2 * B * V * K * F * F
+    out["cfg2_convcheb"] = {
+        "workload": "ConvCheb nside32 (12288 nodes) B32 64->64 K4", "fwd_us": t_fwd * 1e6, "fwd_bwd_us": t_fb * 1e6,
+        "nodes_channels_per_s_fwd": B * V * F / t_fwd, "nodes_channels_per_s_fwd_bwd": B * V * F / t_fb,
+        "fused_layer_algorithmic_bytes": fused_bytes, "fwd_frac_of_hbm_roofline": fused_bytes / t_fwd / 1e9 / hbm_gbs,
+        "fwd_tflops_fp32_equivalent": flops / t_fwd / 1e12,
+    }
     return out
 
 
@@ -337,11 +366,11 @@ def run_ours(args):
         "e2e": {"value": total_samples / e2e_secs, "unit": "samples/s",
                 "h2d_bytes_per_step": (x_host.numel() + y_host.numel()) * 4 * world, "d2h_bytes_per_step": 4 * world},
         "gpu_launches": int(launches),
-        "nodes_channels_per_s": None,
     }
     if world == 1:
         try:
             line.update(time_kernel_rooflines(device, hbm_gbs, bf16_tflops))
+            line["nodes_channels_per_s"] = line["cfg2_convcheb"]["nodes_channels_per_s_fwd"]
         except Exception as exc:  # never lose the headline line
             line["roofline"] = {"error": repr(exc)}
         if not args.no_cpu_baseline:

@@ -303,7 +303,6 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) hop_tile_kernel(const int32_t
 // row-blocks that share a quarter-warp phase read opposite 64-byte halves of their rows (column
 // group XOR parity), which keeps the 128-bit reads bank-conflict free.
 // ---------------------------------------------------------------------------------------------
-constexpr int TEAM_THREADS = DSW_TILE_BLOCKS * 4;   // 4 lanes per row-block
 constexpr int MAX_TEAMS = 5;
 constexpr int PANEL_PAD = 4;        // zero entry steps appended so that the pipeline may over-read
 
@@ -356,13 +355,15 @@ __device__ __forceinline__ void hop_mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
+template <int NT>
 __device__ __forceinline__ void team_sync(int team) {
-  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(TEAM_THREADS) : "memory");
+  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(NT) : "memory");
 }
 
-__device__ __forceinline__ void fma_step(float4 (&acc)[4][4], const float4& w, const float4 (&x)[4]) {
+template <int NJ>
+__device__ __forceinline__ void fma_step(float4 (&acc)[4][NJ], const float4& w, const float4 (&x)[NJ]) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < NJ; ++j) {
     fma4(acc[0][j], w.x, x[j]);
     fma4(acc[1][j], w.y, x[j]);
     fma4(acc[2][j], w.z, x[j]);
@@ -370,10 +371,14 @@ __device__ __forceinline__ void fma_step(float4 (&acc)[4][4], const float4& w, c
   }
 }
 
-template <bool TMA>
-__global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1)
+// LPR = lanes per row-block: 4 (a lane holds 4 rows x 16 channels) or 8 (4 rows x 8 channels: twice the
+// warps per team and half the registers per lane).
+template <bool TMA, int LPR>
+__global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
     hop_team_kernel(const TeamHopPlan P, const HopArgs a, const __grid_constant__ HopMaps maps) {
   extern __shared__ __align__(256) uint8_t tile_smem[];
+  constexpr int TEAM_THREADS = DSW_TILE_BLOCKS * LPR;
+  constexpr int NJ = 16 / LPR;  // float4 columns per lane
   const int tid = threadIdx.x;
   const int tile = blockIdx.x;
   const int blk0 = tile * DSW_TILE_BLOCKS;
@@ -470,7 +475,7 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1)
   int item = item_begin + team;
   if (cnt && team < P.n_teams) {
     if (tt == 0) s_claim[2 * team] = atomicAdd(cnt, 1);
-    team_sync(team);
+    team_sync<TEAM_THREADS>(team);
     item = s_claim[2 * team];
   }
   if (TMA && team < P.n_teams && item < item_end) stage(item);
@@ -488,7 +493,7 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1)
   __syncthreads();
 
   if (team >= P.n_teams) return;
-  const int slot = tt >> 2, l4 = tt & 3, par = slot & 1;
+  const int slot = tt / LPR, lq = tt % LPR, par = slot & 1;
   const int blk = blk0 + slot;
   const bool active = blk < P.n_blocks;
   int my_len = 0;
@@ -497,15 +502,18 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1)
   const int wlen = (__reduce_max_sync(0xffffffffu, my_len) + 1) & ~1;
 
   // byte offsets of this lane's float4 columns inside a staged row: j = 0/2 through cA, j = 1/3 through cB
-  const uint32_t cA = (uint32_t)(l4 * 16) ^ (uint32_t)(par * 64);
-  const uint32_t cB = (uint32_t)(l4 * 16 + 64) ^ (uint32_t)(par * 64);
+  // LPR 4: j = 0/2 through cA, j = 1/3 through cB (XOR parity: the two row-blocks of a quarter-warp phase read
+  // opposite 64-byte halves); LPR 8: the 8 lanes of a row-block read one contiguous 128-byte half per column.
+  const uint32_t cA = LPR == 4 ? ((uint32_t)(lq * 16) ^ (uint32_t)(par * 64)) : (uint32_t)(lq * 16);
+  const uint32_t cB = LPR == 4 ? ((uint32_t)(lq * 16 + 64) ^ (uint32_t)(par * 64)) : (uint32_t)(lq * 16 + 128);
   const uint8_t* xA = xs + cA;
   const uint8_t* xB = xs + cB;
   const uint32_t* po = s_off + slot;
   const float4* pw = s_val + slot;
   // channel of accumulator column j inside the slab
-  int ch[4];
-  ch[0] = (int)(cA >> 2), ch[1] = (int)(cB >> 2), ch[2] = ch[0] + 32, ch[3] = ch[1] + 32;
+  int ch[NJ];
+  ch[0] = (int)(cA >> 2), ch[1] = (int)(cB >> 2);
+  if constexpr (NJ == 4) ch[2] = ch[0] + 32, ch[3] = ch[1] + 32;
 
   uint32_t phase = 0;
   int claim_par = 1;  // slot parity of the claim made during this item (slot 0 held the first one)
@@ -523,16 +531,16 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1)
     // Accumulators start at (beta * Z + G) / alpha (alpha is 1 or 2, so the scaling is exact): the
     // loads are issued here, behind the cp.asyncs, and land while the tile is being staged.
     if (prof) t1 = clock64();
-    float4 acc[4][4];
+    float4 acc[4][NJ];
     {
       const float inv_alpha = 1.f / a.alpha;
       const float zs = a.beta * inv_alpha;
-      bool ok[4][4];
-      int64_t eoff[4][4];
+      bool ok[4][NJ];
+      int64_t eoff[4][NJ];
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NJ; ++j) {
           ok[r][j] = active && (blk * 4 + r) < P.n_rows && ch[j] < slab_f;
           eoff[r][j] = (int64_t)slab * 64 + ch[j];
         }
@@ -540,29 +548,29 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1)
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NJ; ++j) {
           acc[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (a.Z != nullptr && ok[r][j]) acc[r][j] = ldcg4(a.Z + b * a.z_sB + (int64_t)(blk * 4 + r) * a.z_sV + eoff[r][j]);
         }
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < NJ; ++j)
           acc[r][j] = make_float4(acc[r][j].x * zs, acc[r][j].y * zs, acc[r][j].z * zs, acc[r][j].w * zs);
       // batch 2 (adjoint recurrence only): all G loads in flight together
       if (a.G != nullptr) {
-        float4 g[4][4];
+        float4 g[4][NJ];
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < NJ; ++j) {
             g[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ok[r][j]) g[r][j] = ldcg4(a.G + b * a.g_sB + (int64_t)(blk * 4 + r) * a.g_sV + eoff[r][j]);
           }
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
+          for (int j = 0; j < NJ; ++j)
             acc[r][j] = make_float4(fmaf(g[r][j].x, inv_alpha, acc[r][j].x), fmaf(g[r][j].y, inv_alpha, acc[r][j].y),
                                     fmaf(g[r][j].z, inv_alpha, acc[r][j].z), fmaf(g[r][j].w, inv_alpha, acc[r][j].w));
       }
@@ -573,20 +581,22 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1)
       phase ^= 1u;
     } else {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
-      team_sync(team);
+      team_sync<TEAM_THREADS>(team);
     }
 
     if (prof) t2 = clock64();
     {
-      auto load_x = [&](uint32_t o, float4(&x)[4]) {
+      auto load_x = [&](uint32_t o, float4(&x)[NJ]) {
         x[0] = *reinterpret_cast<const float4*>(xA + o);
         x[1] = *reinterpret_cast<const float4*>(xB + o);
-        x[2] = *reinterpret_cast<const float4*>(xA + o + 128);
-        x[3] = *reinterpret_cast<const float4*>(xB + o + 128);
+        if constexpr (NJ == 4) {
+          x[2] = *reinterpret_cast<const float4*>(xA + o + 128);
+          x[3] = *reinterpret_cast<const float4*>(xB + o + 128);
+        }
       };
       // software pipeline: offsets two steps ahead, weights / values one step ahead; the panels carry
       // PANEL_PAD zero steps so the over-reads at the tail are harmless.
-      float4 x0[4], x1[4], w0, w1;
+      float4 x0[NJ], x1[NJ], w0, w1;
       uint32_t o1, o2;
       w0 = pw[0];
       load_x(po[0], x0);
@@ -606,7 +616,7 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1)
 
     if (TMA) {
       // every lane of the team is done reading the staged rows: the next item's transfer may start
-      team_sync(team);
+      team_sync<TEAM_THREADS>(team);
       next_item = cnt ? s_claim[2 * team + claim_par] : item + P.n_teams;
       if (next_item < item_end) stage(next_item);
     }
@@ -618,7 +628,7 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1)
         const int row = blk * 4 + r;
         if (row >= P.n_rows) break;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NJ; ++j) {
           if (ch[j] >= slab_f) continue;
           const int64_t col = (int64_t)slab * 64 + ch[j];
           *reinterpret_cast<float4*>(a.O + b * a.o_sB + row * a.o_sV + col) =
@@ -628,7 +638,7 @@ __global__ void __launch_bounds__(TEAM_THREADS* MAX_TEAMS, 1)
     }
     // every lane of the team is done reading the staged rows before the next item overwrites them
     if (!TMA) {
-      team_sync(team);
+      team_sync<TEAM_THREADS>(team);
       next_item = cnt ? s_claim[2 * team + claim_par] : item + P.n_teams;
     }
     if (prof) {
@@ -702,7 +712,7 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
         P.cnt = rb.hop_cnt + (size_t)(k % HOP_CNT_SLOTS) * rb.n_tiles;
         P.cnt_clear = rb.hop_cnt + (size_t)((k + HOP_CNT_SLOTS / 2) % HOP_CNT_SLOTS) * rb.n_tiles;
         const int64_t extra = g_options[DSW_OPT_HOP_ROWS].load(std::memory_order_relaxed);
-        const int rows = std::min(ceil_div(P.n_items, n_teams), ceil_div(148, rb.n_tiles) + (extra > 0 ? (int)extra : 3));
+        const int rows = std::min(ceil_div(P.n_items, n_teams), ceil_div(148, rb.n_tiles) + (extra > 0 ? (int)extra : 2));
         grid = dim3(rb.n_tiles, std::max(rows, 1));
       }
       // tensor maps of the gather source [B][n_cols][F] with boxes of 1 .. 128 rows x 64 channels
@@ -718,16 +728,18 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
         }
       }
       static std::atomic<bool> attr_set[2] = {{false}, {false}};
-      if (tma) {
-        if (!attr_set[1].exchange(true))
-          DSW_CUDA_TRY(cudaFuncSetAttribute(hop_team_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        hop_team_kernel<true><<<grid, TEAM_THREADS * MAX_TEAMS, smem, st>>>(P, a, maps);
-      } else {
-        if (!attr_set[0].exchange(true))
-          DSW_CUDA_TRY(cudaFuncSetAttribute(hop_team_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        hop_team_kernel<false><<<grid, TEAM_THREADS * MAX_TEAMS, smem, st>>>(P, a, maps);
-      }
-      return check_launch();
+      const bool lpr8 = g_options[DSW_OPT_HOP_LPR].load(std::memory_order_relaxed) == 8;
+      auto launch = [&](auto kern, int threads, int slot) -> int {
+        static std::atomic<bool> attr_done[4] = {{false}, {false}, {false}, {false}};
+        if (!attr_done[slot].exchange(true))
+          DSW_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        kern<<<grid, threads, smem, st>>>(P, a, maps);
+        return check_launch();
+      };
+      if (tma) return lpr8 ? launch(hop_team_kernel<true, 8>, DSW_TILE_BLOCKS * 8 * MAX_TEAMS, 0)
+                           : launch(hop_team_kernel<true, 4>, DSW_TILE_BLOCKS * 4 * MAX_TEAMS, 1);
+      return lpr8 ? launch(hop_team_kernel<false, 8>, DSW_TILE_BLOCKS * 8 * MAX_TEAMS, 2)
+                  : launch(hop_team_kernel<false, 4>, DSW_TILE_BLOCKS * 4 * MAX_TEAMS, 3);
     }
   }
   if (v4 && rb.R == 4 && hop_mode == 3 && off32 && rb.tile_entries_max > 0) {

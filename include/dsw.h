@@ -228,8 +228,9 @@ enum {
   DSW_OPT_CONV_MODE = 7,      /* fp32 -> bf16 hi/lo split of the dense kernels: 0 = packed F2FP (default), 1 = one F2F per value, 2 = integer rounding */
   DSW_OPT_HOP_IPC = 8,        /* work items (sample, 64-channel slab) per hop CTA; 0 = heuristic */
   DSW_OPT_HOP_SMALL_F = 9,    /* planes with at most this many channels take the plain CSR hop (0 = default 8) */
-  DSW_OPT_HOP_ROWS = 10,      /* extra rows of CTAs per tile in the dynamically scheduled hop (0 = default 3) */
-  DSW_OPT_COUNT = 11
+  DSW_OPT_HOP_ROWS = 10,      /* extra rows of CTAs per tile in the dynamically scheduled hop (0 = default 2) */
+  DSW_OPT_HOP_LPR = 11,       /* lanes per row-block of the tile hop kernel: 0 / 4 = four (default), 8 = eight */
+  DSW_OPT_COUNT = 12
 };
 /* Tuning only: with DSW_OPT_DEBUG = 4 the hop kernel sums per-phase SM cycles over its teams
  * (issue staging, wait for tile + Z/G, entry loop, stores, item count). */

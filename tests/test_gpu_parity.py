@@ -93,7 +93,7 @@ def test_convcheb_matches_oracle_seeded(B, nside, Fin, Fout, K, dev, mix_mode):
     assert rel_err(layer.bias.grad, bo.grad) < REL_TOL
 
 
-@pytest.mark.parametrize("hop_kernel", [0, 1, 2, 3], ids=["hop-team", "hop-rb", "hop-csr", "hop-l1tile"])
+@pytest.mark.parametrize("hop_kernel", [0, 1, 2, 3, 8, 12], ids=["hop-team", "hop-rb", "hop-csr", "hop-l1tile", "hop-team-8lanes", "hop-team-static"])
 @pytest.mark.parametrize("chunk_bytes", [0, 1 << 20], ids=["nochunk", "chunk1MB"])
 @pytest.mark.parametrize("save_terms", [True, False], ids=["saved-terms", "recompute"])
 def test_hop_kernels_chunking_and_saved_terms_agree(hop_kernel, chunk_bytes, save_terms, dev, lib):
@@ -113,7 +113,9 @@ def test_hop_kernels_chunking_and_saved_terms_agree(hop_kernel, chunk_bytes, sav
     xo, wo, bo = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
     yo = O.conv_cheb_layer(lap, xo, wo, bo)
     yo.backward(dy)
-    lib.dsw_set_option(0, hop_kernel)
+    lib.dsw_set_option(0, hop_kernel if hop_kernel < 8 else 0)
+    lib.dsw_set_option(11, 8 if hop_kernel == 8 else 0)   # lanes per row-block of the tile kernel
+    lib.dsw_set_option(8, 4 if hop_kernel == 12 else 0)   # static item blocks instead of dynamic claiming
     lib.dsw_set_option(1, chunk_bytes)
     F_.set_save_terms(save_terms)
     try:
@@ -140,7 +142,7 @@ def test_hop_kernels_chunking_and_saved_terms_agree(hop_kernel, chunk_bytes, sav
         for k in range(1, K):
             assert rel_err(terms[k - 1], t[k].reshape(V, Fin, B).permute(2, 0, 1)) < REL_TOL
     finally:
-        for key in (0, 1, 4, 5):
+        for key in (0, 1, 4, 5, 8, 11):
             lib.dsw_set_option(key, 0)
         F_.set_save_terms(True)
 

@@ -50,10 +50,13 @@ def main():
             row.append((ipc, timed(lambda: F_.cheb_terms(x, plan, K), flush)))
         lib.dsw_set_option(OPT_IPC, 0)
         extra = ""
-        for rows in (1, 2, 3, 5, 8):
+        for rows in (1, 3):
             lib.dsw_set_option(OPT_ROWS, rows)
             extra += f"  rows+{rows}={timed(lambda: F_.cheb_terms(x, plan, K), flush):7.1f}"
         lib.dsw_set_option(OPT_ROWS, 0)
+        lib.dsw_set_option(11, 8)
+        extra += f"  8lanes={timed(lambda: F_.cheb_terms(x, plan, K), flush):7.1f}"
+        lib.dsw_set_option(11, 0)
         if F <= 24:
             lib.dsw_set_option(OPT_SMALL_F, 32)
             extra = f"  csr-path {timed(lambda: F_.cheb_terms(x, plan, K), flush):7.1f}"
