@@ -52,8 +52,9 @@ struct dsw_rb {
   float4* tp_val = nullptr;      // [total_steps][32] R = 4 weights
   uint32_t* tp_off = nullptr;    // [total_steps][32] byte offset of the source row inside the staged tile (256 B rows)
   // Dynamic item scheduling of the tile hop kernel: HOP_CNT_SLOTS rotating sets of per-tile claim
-  // counters (all zero between uses) and the host-side launch counter that picks the set.
-  int32_t* hop_cnt = nullptr;               // [HOP_CNT_SLOTS][n_tiles]
+  // counters + one "CTAs gone" word (all zero between launches: the last CTA of a launch clears its
+  // set) and the host-side launch counter that picks the set.
+  int32_t* hop_cnt = nullptr;               // [HOP_CNT_SLOTS][n_tiles + 1]
   std::atomic<uint32_t>* hop_ring = nullptr;
   int32_t* blkptr = nullptr;   // [n_blocks + 1] offsets into ucol / uval panels
   int32_t* ucol = nullptr;     // [total_union]

@@ -252,7 +252,7 @@ static cudaError_t upload_rb(dsw_rb* d, const HostRb& h, cudaStream_t st) {
     if ((e = upload(&tv, h.tp_val, st)) != cudaSuccess) return e;
     d->tp_val = reinterpret_cast<float4*>(tv);
     if ((e = upload(&d->tp_off, h.tp_off, st)) != cudaSuccess) return e;
-    const size_t cnt_bytes = (size_t)HOP_CNT_SLOTS * h.n_tiles * sizeof(int32_t);
+    const size_t cnt_bytes = (size_t)HOP_CNT_SLOTS * (h.n_tiles + 1) * sizeof(int32_t);
     if ((e = cudaMalloc(reinterpret_cast<void**>(&d->hop_cnt), cnt_bytes)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(d->hop_cnt, 0, cnt_bytes, st)) != cudaSuccess) return e;
     d->hop_ring = new std::atomic<uint32_t>(0);

@@ -323,7 +323,7 @@ struct TeamHopPlan {
   int32_t items_per_cta;
   int32_t n_teams;
   int32_t* cnt;           // per-tile claim counters of this launch (dynamic item scheduling) or null
-  int32_t* cnt_clear;     // counter slot this launch zeroes for a later launch
+  int32_t n_ctas;         // CTAs of this launch (the last one to leave zeroes the counters again)
   int32_t debug_skip;     // timing experiments only: 1 = skip staging, 2 = skip the entry loop
 };
 
@@ -403,13 +403,23 @@ __global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
   // Dynamic scheduling: the CTAs of one tile (blockIdx.y = 0 .. gridDim.y - 1) claim its work items
   // from a global counter, so late CTAs share what is left and CTAs that find nothing leave at once.
   int32_t* cnt = P.cnt ? P.cnt + tile : nullptr;
-  if (cnt) {
-    if (tid == 0) {
-      if (P.cnt_clear && blockIdx.y == 0) P.cnt_clear[tile] = 0;
-      s_claim[2 * MAX_TEAMS] = atomicAdd(cnt, 0) >= P.n_items;
+  // Leaving protocol: the counters must be zero again for the next launch that uses this set (stream
+  // order, CUDA-graph replays included).  Every CTA counts itself out on cnt[n_tiles]; the last one —
+  // nobody claims any more — zeroes the whole set.
+  auto leave = [&]() {
+    __threadfence();
+    const int32_t gone = atomicAdd(P.cnt + gridDim.x, 1);
+    if (gone == P.n_ctas - 1) {
+      for (int t = 0; t <= (int)gridDim.x; ++t) P.cnt[t] = 0;
     }
+  };
+  if (cnt) {
+    if (tid == 0) s_claim[2 * MAX_TEAMS] = atomicAdd(cnt, 0) >= P.n_items;
     __syncthreads();
-    if (s_claim[2 * MAX_TEAMS]) return;
+    if (s_claim[2 * MAX_TEAMS]) {
+      if (tid == 0) leave();
+      return;
+    }
   }
 
   // ---- prologue, part 1: the source-row list (TMA: piece list + mbarriers) ----
@@ -652,6 +662,12 @@ __global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
     item = next_item;
     claim_par ^= 1;
   }
+  if (cnt) {
+    // all active teams of the CTA are done claiming (named barrier over the active teams only: the
+    // threads of unused teams have exited)
+    asm volatile("bar.sync 15, %0;" ::"r"(P.n_teams * TEAM_THREADS) : "memory");
+    if (tid == 0) leave();
+  }
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -705,15 +721,15 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
       dim3 grid(rb.n_tiles, ceil_div(P.n_items, ipc));
       // Dynamic scheduling (default): the CTAs of a tile claim items from a per-tile counter.  One CTA
       // per tile plus enough extra rows of CTAs to fill the machine and to share the tiles of the last,
-      // partial round; CTAs that find their tile finished leave before staging anything.  Counter slots
-      // rotate per launch: this launch zeroes the slot that will be used HOP_CNT_SLOTS / 2 launches later.
+      // partial round; CTAs that find their tile finished leave before staging anything.  The counter sets
+      // rotate per launch (concurrent streams get different sets); the last CTA of a launch zeroes its set.
       if (rb.hop_cnt && rb.hop_ring && g_options[DSW_OPT_HOP_IPC].load(std::memory_order_relaxed) == 0) {
         const uint32_t k = rb.hop_ring->fetch_add(1, std::memory_order_relaxed);
-        P.cnt = rb.hop_cnt + (size_t)(k % HOP_CNT_SLOTS) * rb.n_tiles;
-        P.cnt_clear = rb.hop_cnt + (size_t)((k + HOP_CNT_SLOTS / 2) % HOP_CNT_SLOTS) * rb.n_tiles;
+        P.cnt = rb.hop_cnt + (size_t)(k % HOP_CNT_SLOTS) * (rb.n_tiles + 1);
         const int64_t extra = g_options[DSW_OPT_HOP_ROWS].load(std::memory_order_relaxed);
         const int rows = std::min(ceil_div(P.n_items, n_teams), ceil_div(148, rb.n_tiles) + (extra > 0 ? (int)extra : 2));
         grid = dim3(rb.n_tiles, std::max(rows, 1));
+        P.n_ctas = (int32_t)(grid.x * grid.y);
       }
       // tensor maps of the gather source [B][n_cols][F] with boxes of 1 .. 128 rows x 64 channels
       HopMaps maps;

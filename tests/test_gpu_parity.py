@@ -531,6 +531,37 @@ def test_rezero_residual_matches_torch(shape, w0, dev):
     assert rel_err(y2, (wide[..., : shape[2]].cpu() * w + s).numpy()) < 1e-6
 
 
+def test_hops_replay_in_a_cuda_graph(dev):
+    """The dynamically scheduled hop kernel keeps claim counters in the plan; they must be back to
+    zero after every launch so that replays of a captured CUDA graph (same counter set every time)
+    compute the same thing as eager launches."""
+    from deepsphere_weather_b200 import functional as F_
+    from deepsphere_weather_b200 import graphs as G
+
+    torch.manual_seed(5)
+    lap = G.healpix_laplacian(8).to(dev)
+    plan = F_.plan_for(lap)
+    B, V, F, K = 5, lap.shape[0], 64, 4
+    x = torch.randn(B, V, F, device=dev)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):  # warm-up outside the capture (function attributes, allocator pools)
+            F_.cheb_terms(x, plan, K)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = F_.cheb_terms(x, plan, K)
+    for rep in range(3):
+        xn = torch.randn(B, V, F, device=dev)
+        x.copy_(xn)
+        g.replay()
+        torch.cuda.synchronize()
+        got = out.clone()
+        want = F_.cheb_terms(xn, plan, K)
+        assert torch.equal(got, want), f"replay {rep}"
+
+
 def test_cfg5_equiangular_k6_c128_matches_oracle(dev):
     """cfg5: equiangular 400 x 200 (80 000 nodes, row-major, k-NN 20), ConvCheb K = 6, Cin = Cout = 128:
     the irregular-degree / poor-locality stress case.  Forward, dx, dW, dbias against the oracle."""
