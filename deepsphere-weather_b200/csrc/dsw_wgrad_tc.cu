@@ -120,6 +120,7 @@ struct WtcArgs {
   int32_t otiles;      // column tiles per Fout-side plane
   int32_t dbg;         // timing experiments only (DSW_OPT_DEBUG bits 32..256; results become wrong)
   int32_t cmode;       // split_pair mode
+  int32_t pp;          // Fout-side planes per CTA tile (TMA kernel only): > 1 = the tile spans pp whole planes of Fout <= 128 columns
 };
 
 __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WtcArgs P) {
@@ -409,7 +410,10 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (size_t)S * stage_bytes + 8 * (3 * S));
 
   const int mtile = blockIdx.x, split = blockIdx.z;
-  const int kb_plane = blockIdx.y / P.otiles, ntile = blockIdx.y - kb_plane * P.otiles;
+  // N tile: either one column tile of one Fout-side plane, or (pp > 1) pp whole planes side by side
+  const bool span = P.pp > 1;
+  const int kb_plane = span ? blockIdx.y * P.pp : blockIdx.y / P.otiles;
+  const int ntile = span ? 0 : blockIdx.y - kb_plane * P.otiles;
   const int n_half = a.Ka * P.ftiles;
   const int64_t r_begin = (int64_t)split * P.kb_per_split * KB;
   const int64_t r_end = (r_begin + (int64_t)P.kb_per_split * KB < a.N) ? r_begin + (int64_t)P.kb_per_split * KB : a.N;
@@ -477,7 +481,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
           *reinterpret_cast<uint2*>(hi_img + off) = qh;
           *reinterpret_cast<uint2*>(lo_img + off) = ql;
         }
-        if (do_bias && u >= 2) {
+        if (do_bias && u >= 2 && (u - 2) * 64 < a.Fout) {  // (pp > 1: only the units of plane 0 are dy itself)
           float4& b = bsum[u - 2];
 #pragma unroll
           for (int i = 0; i < 4; ++i) b.x += v[u][i].x, b.y += v[u][i].y, b.z += v[u][i].z, b.w += v[u][i].w;
@@ -492,7 +496,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
     if (do_bias) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (j < nb) {
+        if (j < nb && j * 64 < a.Fout) {
           atomicAdd(&bias_acc[j * 64 + q * 4 + 0], bsum[j].x);
           atomicAdd(&bias_acc[j * 64 + q * 4 + 1], bsum[j].y);
           atomicAdd(&bias_acc[j * 64 + q * 4 + 2], bsum[j].z);
@@ -532,15 +536,18 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
         for (int e = 0; e < 16; ++e) r[e] = 0u;
       }
       if (m < 0) continue;
-      const int o0 = o_base + ch * 16;
+      // pp > 1: Fout is a multiple of 64, so a 16-column chunk lies inside one plane
+      const int cpl = span ? (ch * 16) / a.Fout : 0;
+      const int o0 = span ? (ch * 16) - cpl * a.Fout : o_base + ch * 16;
+      const int64_t mm = m + cpl;
       if (o0 + 15 < a.Fout && (a.Fout & 3) == 0) {
 #pragma unroll
         for (int e = 0; e < 16; e += 4)
-          *reinterpret_cast<uint4*>(Pp + m * a.Fout + o0 + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+          *reinterpret_cast<uint4*>(Pp + mm * a.Fout + o0 + e) = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
       } else {
 #pragma unroll
         for (int e = 0; e < 16; ++e)
-          if (o0 + e < a.Fout) Pp[m * a.Fout + o0 + e] = __uint_as_float(r[e]);
+          if (o0 + e < a.Fout) Pp[mm * a.Fout + o0 + e] = __uint_as_float(r[e]);
       }
     }
   } else if (warp == 8) {
@@ -552,7 +559,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
         hk[h] = half_ok[h] ? ht / P.ftiles : 0;
         hf[h] = half_ok[h] ? (ht - hk[h] * P.ftiles) * 64 : 0;
       }
-      const CUtensorMap* ymap = &Q.maps[a.Ka + kb_plane];
+      const int upp = span ? a.Fout / 64 : 0;  // units per plane when the tile spans planes
             for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % S;
         const uint32_t use = (uint32_t)(kb / S);
@@ -574,7 +581,11 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
             tma_load_3d(st + h * UNIT, &Q.maps[hk[h]], hf[h], (int)(n0 - (int64_t)bb * a.rows_per_batch), bb, raw_full(s));
           }
         }
-        for (int j = 0; j < ((P.dbg & 64) ? 0 : nb); ++j) tma_load_2d(st + (2 + j) * UNIT, ymap, o_base + 64 * j, (int)n0, raw_full(s));
+        for (int j = 0; j < ((P.dbg & 64) ? 0 : nb); ++j) {
+          const int pl = span ? j / upp : 0;
+          const int col = span ? (j - pl * upp) * 64 : o_base + 64 * j;
+          tma_load_2d(st + (2 + j) * UNIT, &Q.maps[a.Ka + kb_plane + pl], col, (int)n0, raw_full(s));
+        }
       }
     }
   } else if (lane == 0) {
@@ -649,10 +660,22 @@ static size_t smem_bytes_for(int nb) { return (size_t)STAGES * (2 * 2 * BLK + 2 
 
 }  // namespace wtc
 
+// Planes per N tile.  The adjoint form (Kb = K planes on the Fout side) with narrow planes would give
+// N tiles of only 64 / 128 columns — half or a quarter of the MMA work per byte staged; the TMA kernel
+// then lets one tile span 256 / Fout whole planes.
+static int wgrad_span_planes(int32_t Kb, int32_t Fin, int32_t Fout) {
+  if (Kb < 2 || (Fout != 64 && Fout != 128) || (Fin & 3)) return 1;
+  if (g_options[DSW_OPT_NO_TMA].load(std::memory_order_relaxed) != 0) return 1;
+  int pp = 256 / Fout;
+  while (pp > 1 && Kb % pp) pp >>= 1;
+  return pp;
+}
+
 static void wgrad_tc_geometry(int64_t N, int32_t Ka, int32_t Kb, int32_t Fin, int32_t Fout, int& BN, int& ntiles,
                               int& mtiles, int& nsplit, int& kb_per_split) {
-  BN = std::min(256, (Fout + 15) / 16 * 16);
-  ntiles = Kb * ((Fout + BN - 1) / BN);
+  const int pp = wgrad_span_planes(Kb, Fin, Fout);
+  BN = pp > 1 ? pp * Fout : std::min(256, (Fout + 15) / 16 * 16);
+  ntiles = pp > 1 ? Kb / pp : Kb * ((Fout + BN - 1) / BN);
   const int ftiles = (Fin + 63) / 64;
   mtiles = (Ka * ftiles + 1) / 2;
   const int64_t total_kb = (N + wtc::KB - 1) / wtc::KB;
@@ -681,7 +704,8 @@ int launch_wgrad_tc(const WgradArgs& a, size_t partial_bytes, cudaStream_t st) {
   P.w = a;
   int ntiles, mtiles, nsplit;
   wgrad_tc_geometry(a.N, a.Ka, a.Kb, a.Fin, a.Fout, P.BN, ntiles, mtiles, nsplit, P.kb_per_split);
-  P.otiles = ntiles / a.Kb;
+  P.pp = wgrad_span_planes(a.Kb, a.Fin, a.Fout);
+  P.otiles = P.pp > 1 ? 1 : ntiles / a.Kb;
   P.dbg = (int)g_options[DSW_OPT_DEBUG].load(std::memory_order_relaxed) & 0x1E0;
   P.cmode = split_mode();
   P.w.nsplit = nsplit;
@@ -704,6 +728,7 @@ int launch_wgrad_tc(const WgradArgs& a, size_t partial_bytes, cudaStream_t st) {
       return check_launch();
     }
   }
+  if (P.pp > 1) return launch_wgrad_simt(P.w, st);  // the register-path kernel does not span planes (same partial layout)
   const size_t smem = wtc::smem_bytes_for(P.nb);
   static std::atomic<bool> attr_set{false};
   if (!attr_set.exchange(true))
