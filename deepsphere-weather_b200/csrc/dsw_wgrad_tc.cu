@@ -88,6 +88,63 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA pair (cta_group::2) variants: the two CTAs of a cluster share one 256-row MMA ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t slot_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrives (once the MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// arrive on the barrier at the same offset in the pair's leader CTA (rank 0)
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAITC_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONEC_%=;\n\t"
+      "bra WAITC_%=;\n\t"
+      "DONEC_%=:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
 // MN-major SWIZZLE_128B descriptor: `lbo` = bytes between 64-element MN blocks, `sbo` = bytes between
 // 8-row K groups (cute::UMMA::make_umma_desc<Major::MN>: ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO))).
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -389,6 +446,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 
+// PAIR: two CTAs of a cluster (consecutive M tiles, same N tile and row range) issue one
+// tcgen05.mma.cta_group::2 of 256 x BN: each CTA stages, converts and feeds its own 128 rows of the M side
+// and only HALF of the N-side units — a third less shared-memory traffic per MMA cycle, which is what
+// bounds this kernel.  Rank 0 issues the MMAs once both CTAs' converters have arrived on its barrier; the
+// commits are multicast to both CTAs.
+// Role timing for tuning (DSW_OPT_DEBUG bit 512): cycles summed over CTAs, read by dsw_debug_dense_counters.
+__device__ unsigned long long g_wgrad_prof[8];
+
+template <bool PAIR>
 __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_constant__ WtmaArgs Q) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ float bias_acc[256];
@@ -397,7 +463,10 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int BN = P.BN, nb = P.nb, S = Q.stages;
   const int cmode = P.cmode;
-  const int U = 2 + nb;  // units per row block: A half 0, A half 1, B blocks
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int nbl = PAIR ? nb / 2 : nb;          // N-side units staged by this CTA
+  const int ub0 = PAIR ? (int)rank * nbl : 0;  // their first unit index inside the N tile
+  const int U = 2 + nbl;  // units per row block: A half 0, A half 1, local B blocks
   const uint32_t stage_bytes = (uint32_t)U * UNIT;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -424,7 +493,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
   if (t == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(raw_full(s), 1);
-      mbar_init(full(s), T_CONV / 32);  // one elected arrival per converter warp
+      mbar_init(full(s), (PAIR ? 2 : 1) * (T_CONV / 32));  // one elected arrival per converter warp (of both CTAs)
       mbar_init(empty(s), 1);
     }
     fence_mbar_init();
@@ -435,17 +504,21 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
     for (int s = 0; s < S; ++s)
       for (int i = t; i < UNIT / 16; i += T_THREADS)
         *reinterpret_cast<uint4*>(smem_gen + (size_t)s * stage_bytes + UNIT + i * 16) = make_uint4(0, 0, 0, 0);
-  if (warp == 9) tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+  if (warp == 9) {
+    if (PAIR) tmem_alloc2(tmem_slot, (uint32_t)P.tmem_cols);
+    else tmem_alloc(tmem_slot, (uint32_t)P.tmem_cols);
+  }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anyone arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
   if (warp < 8) {
     // ================= converters =================
     const int q = t & 15, r0 = t >> 4;  // float4 column, rows r0 + 16 i
-    const bool do_bias = (mtile == 0) && (kb_plane == 0) && (a.dbias != nullptr);
+    const bool do_bias = ((PAIR ? mtile >> 1 : mtile) == 0) && (kb_plane == 0) && (a.dbias != nullptr);
     float4 bsum[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) bsum[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -453,9 +526,20 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
       const int s = kb % S;
       const uint32_t ph = (uint32_t)(kb / S) & 1;
       uint8_t* st = smem_gen + (size_t)s * stage_bytes;
+      const bool prof = (P.dbg & 512) && t == 0;
+      long long tp0 = 0;
+      if (prof) tp0 = clock64();
       mbar_wait(raw_full(s), ph);
+      if (prof) {
+        const long long tp1 = clock64();
+        atomicAdd(&g_wgrad_prof[0], (unsigned long long)(tp1 - tp0));  // converters waiting for the TMA
+        tp0 = tp1;
+      }
       if (P.dbg & 128) {  // timing experiment: no conversion
-        if (lane == 0) mbar_arrive(full(s));
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_leader(full(s));
+          else mbar_arrive(full(s));
+        }
         continue;
       }
       float4 v[6][4];
@@ -481,7 +565,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
           *reinterpret_cast<uint2*>(hi_img + off) = qh;
           *reinterpret_cast<uint2*>(lo_img + off) = ql;
         }
-        if (do_bias && u >= 2 && (u - 2) * 64 < a.Fout) {  // (pp > 1: only the units of plane 0 are dy itself)
+        if (do_bias && u >= 2 && (ub0 + u - 2) * 64 < a.Fout) {  // (pp > 1: only the units of plane 0 are dy itself)
           float4& b = bsum[u - 2];
 #pragma unroll
           for (int i = 0; i < 4; ++i) b.x += v[u][i].x, b.y += v[u][i].y, b.z += v[u][i].z, b.w += v[u][i].w;
@@ -489,18 +573,25 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(full(s));
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(full(s));
+        else mbar_arrive(full(s));
+      }
+      if (prof) {
+        atomicAdd(&g_wgrad_prof[1], (unsigned long long)(clock64() - tp0));  // converting one stage
+        atomicAdd(&g_wgrad_prof[2], 1ull);                                   // stages
+      }
     }
 
     // ---- dbias partial (fp32, CTA-local reduction through shared memory) ----
     if (do_bias) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (j < nb && j * 64 < a.Fout) {
-          atomicAdd(&bias_acc[j * 64 + q * 4 + 0], bsum[j].x);
-          atomicAdd(&bias_acc[j * 64 + q * 4 + 1], bsum[j].y);
-          atomicAdd(&bias_acc[j * 64 + q * 4 + 2], bsum[j].z);
-          atomicAdd(&bias_acc[j * 64 + q * 4 + 3], bsum[j].w);
+        if (j < nbl && (ub0 + j) * 64 < a.Fout) {
+          atomicAdd(&bias_acc[(ub0 + j) * 64 + q * 4 + 0], bsum[j].x);
+          atomicAdd(&bias_acc[(ub0 + j) * 64 + q * 4 + 1], bsum[j].y);
+          atomicAdd(&bias_acc[(ub0 + j) * 64 + q * 4 + 2], bsum[j].z);
+          atomicAdd(&bias_acc[(ub0 + j) * 64 + q * 4 + 3], bsum[j].w);
         }
       }
     }
@@ -509,7 +600,8 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
     // ================= epilogue: TMEM -> partial[split] =================
     const int64_t prow = (int64_t)a.K * a.Fin + 1;
     float* __restrict__ Pp = a.partial + (int64_t)split * prow * a.Fout;
-    if (do_bias && t < BN && o_base + t < a.Fout) Pp[(prow - 1) * a.Fout + o_base + t] = bias_acc[t];
+    if (do_bias && t < BN && (t >> 6) >= ub0 && (t >> 6) < ub0 + nbl && o_base + t < a.Fout)
+      Pp[(prow - 1) * a.Fout + o_base + t] = bias_acc[t];
 
     if (nkb > 0) {
       const int last = nkb - 1;
@@ -563,10 +655,13 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
             for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % S;
         const uint32_t use = (uint32_t)(kb / S);
+        long long tq0 = 0;
+        if (P.dbg & 512) tq0 = clock64();
         if (use > 0) mbar_wait(empty(s), (use - 1) & 1);
+        if (P.dbg & 512) atomicAdd(&g_wgrad_prof[3], (unsigned long long)(clock64() - tq0));  // producer waiting for a free stage
         const uint32_t st = smem_base + s * stage_bytes;
         const int64_t n0 = r_begin + (int64_t)kb * KB;
-        const uint32_t tx_now = (P.dbg & 32 ? 0u : (uint32_t)(half_ok[1] ? 2 : 1) * UNIT) + (P.dbg & 64 ? 0u : (uint32_t)nb * UNIT);
+        const uint32_t tx_now = (P.dbg & 32 ? 0u : (uint32_t)(half_ok[1] ? 2 : 1) * UNIT) + (P.dbg & 64 ? 0u : (uint32_t)nbl * UNIT);
         if (tx_now == 0) {
           mbar_arrive(raw_full(s));
           continue;
@@ -581,22 +676,27 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
             tma_load_3d(st + h * UNIT, &Q.maps[hk[h]], hf[h], (int)(n0 - (int64_t)bb * a.rows_per_batch), bb, raw_full(s));
           }
         }
-        for (int j = 0; j < ((P.dbg & 64) ? 0 : nb); ++j) {
-          const int pl = span ? j / upp : 0;
-          const int col = span ? (j - pl * upp) * 64 : o_base + 64 * j;
+        for (int j = 0; j < ((P.dbg & 64) ? 0 : nbl); ++j) {
+          const int g = ub0 + j;  // unit index inside the N tile
+          const int pl = span ? g / upp : 0;
+          const int col = span ? (g - pl * upp) * 64 : o_base + 64 * g;
           tma_load_2d(st + (2 + j) * UNIT, &Q.maps[a.Ka + kb_plane + pl], col, (int)n0, raw_full(s));
         }
       }
     }
-  } else if (lane == 0) {
-    // ================= MMA issuer =================
+  } else if (lane == 0 && rank == 0) {
+    // ================= MMA issuer (pair: the leader CTA only) =================
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
     const uint32_t lbo = (uint32_t)UNIT;  // between 64-channel blocks (each unit = [hi | lo])
     const uint32_t sbo = 1024u;           // between 8-row groups
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % S;
-      mbar_wait(full(s), (uint32_t)(kb / S) & 1);
+      long long tm0 = 0;
+      if (P.dbg & 512) tm0 = clock64();
+      if (PAIR) mbar_wait_cluster(full(s), (uint32_t)(kb / S) & 1);
+      else mbar_wait(full(s), (uint32_t)(kb / S) & 1);
+      if (P.dbg & 512) atomicAdd(&g_wgrad_prof[4], (unsigned long long)(clock64() - tm0));  // MMA issuer waiting for operands
       tc_fence_after();
       const uint32_t st = smem_base + s * stage_bytes;
       const uint32_t Ah = st, Al = st + UNIT / 2, Bh = st + 2u * UNIT, Bl = Bh + UNIT / 2;
@@ -604,16 +704,27 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
         const uint32_t adv = (uint32_t)ks * 2048u;  // 16 rows = two 8-row groups
         const uint64_t dAh = make_desc_mn(Ah + adv, lbo, sbo), dAl = make_desc_mn(Al + adv, lbo, sbo);
         const uint64_t dBh = make_desc_mn(Bh + adv, lbo, sbo), dBl = make_desc_mn(Bl + adv, lbo, sbo);
-        umma_bf16(tmem_base, dAh, dBh, idesc, (kb | ks) != 0);
-        umma_bf16(tmem_base, dAh, dBl, idesc, 1u);
-        umma_bf16(tmem_base, dAl, dBh, idesc, 1u);
+        if (PAIR) {
+          umma_bf16_pair(tmem_base, dAh, dBh, idesc, (kb | ks) != 0);
+          umma_bf16_pair(tmem_base, dAh, dBl, idesc, 1u);
+          umma_bf16_pair(tmem_base, dAl, dBh, idesc, 1u);
+        } else {
+          umma_bf16(tmem_base, dAh, dBh, idesc, (kb | ks) != 0);
+          umma_bf16(tmem_base, dAh, dBl, idesc, 1u);
+          umma_bf16(tmem_base, dAl, dBh, idesc, 1u);
+        }
       }
-      umma_commit(empty(s));
+      if (PAIR) umma_commit_pair(empty(s));
+      else umma_commit(empty(s));
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+  if (PAIR) cluster_sync_all();  // both CTAs are done with the shared accumulator / the peer's operands
+  if (warp == 9) {
+    if (PAIR) tmem_dealloc2(tmem_base, (uint32_t)P.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)P.tmem_cols);
+  }
 }
 
 static int tma_stages_for(int nb) {
@@ -706,7 +817,7 @@ int launch_wgrad_tc(const WgradArgs& a, size_t partial_bytes, cudaStream_t st) {
   wgrad_tc_geometry(a.N, a.Ka, a.Kb, a.Fin, a.Fout, P.BN, ntiles, mtiles, nsplit, P.kb_per_split);
   P.pp = wgrad_span_planes(a.Kb, a.Fin, a.Fout);
   P.otiles = P.pp > 1 ? 1 : ntiles / a.Kb;
-  P.dbg = (int)g_options[DSW_OPT_DEBUG].load(std::memory_order_relaxed) & 0x1E0;
+  P.dbg = (int)g_options[DSW_OPT_DEBUG].load(std::memory_order_relaxed) & 0x3E0;
   P.cmode = split_mode();
   P.w.nsplit = nsplit;
   P.nb = (P.BN + 63) / 64;
@@ -721,10 +832,29 @@ int launch_wgrad_tc(const WgradArgs& a, size_t partial_bytes, cudaStream_t st) {
     Q.c = P;
     Q.stages = wtc::tma_stages_for(P.nb);
     if (wtc::encode_maps(a, &Q)) {
-      static std::atomic<bool> attr_tma{false};
-      if (!attr_tma.exchange(true))
-        DSW_CUDA_TRY(cudaFuncSetAttribute(wtc::wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-      wtc::wgrad_tma_kernel<<<grid, wtc::T_THREADS, wtc::tma_smem_bytes_for(P.nb), st>>>(Q);
+      // CTA pairs when consecutive M tiles exist in pairs and the N tile splits into two halves of whole units
+      // (measured 5-50 % SLOWER than single CTAs — each SM's shared memory still serves its half of B to both
+      // tensor cores, so the per-SM read traffic does not drop, and the cross-CTA barriers add latency — hence
+      // opt-in only: DSW_OPT_WGRAD_PAIR = 1)
+      const bool pair = (mtiles % 2 == 0) && (P.nb % 2 == 0) && g_options[DSW_OPT_WGRAD_PAIR].load(std::memory_order_relaxed) == 1;
+      static std::atomic<bool> attr_tma[2] = {{false}, {false}};
+      if (pair) {
+        const int nbl = P.nb / 2;
+        Q.stages = wtc::tma_stages_for(nbl);
+        if (!attr_tma[1].exchange(true))
+          DSW_CUDA_TRY(cudaFuncSetAttribute(wtc::wgrad_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid, cfg.blockDim = dim3(wtc::T_THREADS), cfg.dynamicSmemBytes = wtc::tma_smem_bytes_for(nbl), cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr, cfg.numAttrs = 1;
+        DSW_CUDA_TRY(cudaLaunchKernelEx(&cfg, wtc::wgrad_tma_kernel<true>, Q));
+        return check_launch();
+      }
+      if (!attr_tma[0].exchange(true))
+        DSW_CUDA_TRY(cudaFuncSetAttribute(wtc::wgrad_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      wtc::wgrad_tma_kernel<false><<<grid, wtc::T_THREADS, wtc::tma_smem_bytes_for(P.nb), st>>>(Q);
       return check_launch();
     }
   }
@@ -739,3 +869,15 @@ int launch_wgrad_tc(const WgradArgs& a, size_t partial_bytes, cudaStream_t st) {
 }
 
 }  // namespace dsw
+
+extern "C" int dsw_debug_dense_counters(uint64_t* out8, int reset) {
+  if (!out8) return DSW_ERR_BAD_ARGUMENT;
+  unsigned long long h[8];
+  DSW_CUDA_TRY(cudaMemcpyFromSymbol(h, dsw::wtc::g_wgrad_prof, sizeof(h)));
+  for (int i = 0; i < 8; ++i) out8[i] = h[i];
+  if (reset) {
+    unsigned long long z[8] = {};
+    DSW_CUDA_TRY(cudaMemcpyToSymbol(dsw::wtc::g_wgrad_prof, z, sizeof(z)));
+  }
+  return DSW_OK;
+}

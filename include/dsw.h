@@ -230,11 +230,15 @@ enum {
   DSW_OPT_HOP_SMALL_F = 9,    /* planes with at most this many channels take the plain CSR hop (0 = default 8) */
   DSW_OPT_HOP_ROWS = 10,      /* extra rows of CTAs per tile in the dynamically scheduled hop (0 = default 2) */
   DSW_OPT_HOP_LPR = 11,       /* lanes per row-block of the tile hop kernel: 0 / 4 = four (default), 8 = eight */
-  DSW_OPT_COUNT = 12
+  DSW_OPT_WGRAD_PAIR = 12,    /* 1 = pair CTAs (tcgen05 cta_group::2, 256-row MMAs) in the weight-gradient kernel; measured slower, default off */
+  DSW_OPT_COUNT = 13
 };
 /* Tuning only: with DSW_OPT_DEBUG = 4 the hop kernel sums per-phase SM cycles over its teams
  * (issue staging, wait for tile + Z/G, entry loop, stores, item count). */
 int dsw_debug_counters(uint64_t* out8, int reset);
+/* Tuning only: with DSW_OPT_DEBUG bit 512 the weight-gradient kernel sums role cycles over its CTAs (converters
+ * waiting for the TMA, converting, stage count, producer waiting for a free stage, MMA issuer waiting). */
+int dsw_debug_dense_counters(uint64_t* out8, int reset);
 int dsw_set_option(int key, int64_t value);
 int64_t dsw_get_option(int key);
 

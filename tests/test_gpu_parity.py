@@ -472,6 +472,29 @@ def test_full_size_pool_round_trips(dev):
     assert rel_err(L.HealpixAvgPool(4)(L.HealpixAvgUnpool(4)(ya))[0], ya) < 1e-6
 
 
+def test_wgrad_cta_pairs_match_single_ctas(dev, lib):
+    """The opt-in tcgen05 cta_group::2 weight-gradient path (two CTAs share 256-row MMAs) computes the
+    same dW as the single-CTA path."""
+    from deepsphere_weather_b200 import layers as L
+
+    torch.manual_seed(11)
+    B, V, Fin, Fout = 2, 1500, 192, 256   # M side = dy channels (256 -> two M tiles), N side = x channels
+    x, dy = torch.randn(B, V, Fin, device=dev), torch.randn(B, V, Fout, device=dev)
+    lin = L.NodeLinear(Fin, Fout).to(dev)
+    grads = []
+    try:
+        for pair in (0, 1):
+            lib.dsw_set_option(12, pair)
+            lin.zero_grad(set_to_none=True)
+            lin(x).backward(dy)
+            grads.append(lin.weight.grad.clone())
+    finally:
+        lib.dsw_set_option(12, 0)
+    ref = torch.einsum("bvo,bvf->of", dy.double().cpu(), x.double().cpu())
+    assert rel_err(grads[0], ref) < REL_TOL
+    assert rel_err(grads[1], ref) < REL_TOL
+
+
 @pytest.mark.parametrize("B,V,Fin,Fout", [(3, 768, 21, 128), (2, 640, 128, 256), (2, 200, 64, 2), (1, 130, 7, 5)])
 def test_node_linear_matches_torch(B, V, Fin, Fout, dev, mix_mode):
     """The ResBlock skip connection (reference my_models_graph.py:196-201 uses torch.nn.Linear) on the
