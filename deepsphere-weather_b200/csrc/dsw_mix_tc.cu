@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256) mix_tc_prep_kernel(TcArgs P, uint8_t* __r
 // the epilogue of the previous tile drains the other accumulator.
 // ---------------------------------------------------------------------------------------------
 constexpr int N_CONV_WARPS = 8;
-constexpr int WARP_BLOAD = 8, WARP_MMA = 9, WARP_EPI0 = 10;
+constexpr int WARP_BLOAD = 8, WARP_MMA = 9;  // warps 10-13: epilogue
 constexpr int THREADS2 = 32 * 14;
 
 template <bool VEC4>
@@ -746,7 +746,7 @@ static bool encode_a_maps(const MixArgs& a, TmaArgs* Q) {
   Q->rank = flat ? 2 : 3;
   for (int p = 0; p < a.P; ++p) {
     if (a.a_sV[p] < a.Ka) return false;
-    uint64_t dims[3], strides[2];
+    uint64_t dims[3] = {1, 1, 1}, strides[2] = {0, 0};
     const uint32_t box[3] = {(uint32_t)BKB, (uint32_t)BM, 1};
     if (flat) {
       dims[0] = (uint64_t)a.Ka, dims[1] = (uint64_t)a.N;

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) hop_tile_kernel(const int32_t
                                                                     const int32_t* __restrict__ ucol,
                                                                     const float4* __restrict__ uval, int32_t n_blocks,
                                                                     int32_t n_rows, int32_t ns, HopArgs a) {
-  extern __shared__ __align__(16) uint8_t tile_smem[];
+  extern __shared__ __align__(256) uint8_t tile_smem[];
   const int tid = threadIdx.x;
   const int blk0 = blockIdx.x * TILE_BLOCKS;
   const int blk1 = min(blk0 + TILE_BLOCKS, n_blocks);
@@ -533,7 +533,6 @@ __global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
     int next_item = item_end;
     const int b = item / P.n_slabs, slab = item - b * P.n_slabs;
     const int slab_f = min(64, a.F - slab * 64);       // channels in this slab (multiple of 4)
-    const int cpr = slab_f >> 2;                        // 16-byte chunks per row
     const bool prof = (P.debug_skip == 4) && (tt == 0);
     long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
     if (prof) t0 = clock64();
@@ -743,7 +742,6 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
           tma = (1 << j) > A.n_cols ? (maps.m[j] = maps.m[j - 1], true) : encode_f32_map(&maps.m[j], a.X, 3, dims, strides, box);
         }
       }
-      static std::atomic<bool> attr_set[2] = {{false}, {false}};
       const bool lpr8 = g_options[DSW_OPT_HOP_LPR].load(std::memory_order_relaxed) == 8;
       auto launch = [&](auto kern, int threads, int slot) -> int {
         static std::atomic<bool> attr_done[4] = {{false}, {false}, {false}, {false}};

@@ -481,6 +481,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
   const int mtile = blockIdx.x, split = blockIdx.z;
   // N tile: either one column tile of one Fout-side plane, or (pp > 1) pp whole planes side by side
   const bool span = P.pp > 1;
+  const int Fu = (a.Fout + 63) / 64 * 64;  // plane width in whole units (span: each plane starts a new unit)
   const int kb_plane = span ? blockIdx.y * P.pp : blockIdx.y / P.otiles;
   const int ntile = span ? 0 : blockIdx.y - kb_plane * P.otiles;
   const int n_half = a.Ka * P.ftiles;
@@ -565,7 +566,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
           *reinterpret_cast<uint2*>(hi_img + off) = qh;
           *reinterpret_cast<uint2*>(lo_img + off) = ql;
         }
-        if (do_bias && u >= 2 && (ub0 + u - 2) * 64 < a.Fout) {  // (pp > 1: only the units of plane 0 are dy itself)
+        if (do_bias && u >= 2 && (ub0 + u - 2) * 64 < Fu) {  // (pp > 1: only the units of plane 0 are dy itself)
           float4& b = bsum[u - 2];
 #pragma unroll
           for (int i = 0; i < 4; ++i) b.x += v[u][i].x, b.y += v[u][i].y, b.z += v[u][i].z, b.w += v[u][i].w;
@@ -587,7 +588,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
     if (do_bias) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (j < nbl && (ub0 + j) * 64 < a.Fout) {
+        if (j < nbl && (ub0 + j) * 64 < Fu) {
           atomicAdd(&bias_acc[(ub0 + j) * 64 + q * 4 + 0], bsum[j].x);
           atomicAdd(&bias_acc[(ub0 + j) * 64 + q * 4 + 1], bsum[j].y);
           atomicAdd(&bias_acc[(ub0 + j) * 64 + q * 4 + 2], bsum[j].z);
@@ -628,9 +629,9 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
         for (int e = 0; e < 16; ++e) r[e] = 0u;
       }
       if (m < 0) continue;
-      // pp > 1: Fout is a multiple of 64, so a 16-column chunk lies inside one plane
-      const int cpl = span ? (ch * 16) / a.Fout : 0;
-      const int o0 = span ? (ch * 16) - cpl * a.Fout : o_base + ch * 16;
+      // pp > 1: planes start on unit (64-column) boundaries, so a 16-column chunk lies inside one plane
+      const int cpl = span ? (ch * 16) / Fu : 0;
+      const int o0 = span ? (ch * 16) - cpl * Fu : o_base + ch * 16;
       const int64_t mm = m + cpl;
       if (o0 + 15 < a.Fout && (a.Fout & 3) == 0) {
 #pragma unroll
@@ -651,7 +652,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
         hk[h] = half_ok[h] ? ht / P.ftiles : 0;
         hf[h] = half_ok[h] ? (ht - hk[h] * P.ftiles) * 64 : 0;
       }
-      const int upp = span ? a.Fout / 64 : 0;  // units per plane when the tile spans planes
+      const int upp = span ? Fu / 64 : 0;  // units per plane when the tile spans planes
             for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % S;
         const uint32_t use = (uint32_t)(kb / S);
@@ -748,7 +749,7 @@ static bool encode_maps(const WgradArgs& a, WtmaArgs* Q) {
   Q->rank = flat ? 2 : 3;
   const uint32_t box[3] = {64u, (uint32_t)KB, 1u};
   for (int k = 0; k < a.Ka; ++k) {
-    uint64_t dims[3], strides[2];
+    uint64_t dims[3] = {1, 1, 1}, strides[2] = {0, 0};
     dims[0] = (uint64_t)a.Fin;
     if (flat) {
       dims[1] = (uint64_t)a.N, strides[0] = (uint64_t)a.t_sV[k] * 4;
@@ -773,11 +774,11 @@ static size_t smem_bytes_for(int nb) { return (size_t)STAGES * (2 * 2 * BLK + 2 
 
 // Planes per N tile.  The adjoint form (Kb = K planes on the Fout side) with narrow planes would give
 // N tiles of only 64 / 128 columns — half or a quarter of the MMA work per byte staged; the TMA kernel
-// then lets one tile span 256 / Fout whole planes.
+// then lets one tile span 256 / ceil64(Fout) whole planes (zero-filled past Fout inside each plane).
 static int wgrad_span_planes(int32_t Kb, int32_t Fin, int32_t Fout) {
-  if (Kb < 2 || (Fout != 64 && Fout != 128) || (Fin & 3)) return 1;
+  if (Kb < 2 || Fout > 128 || (Fout & 3) || (Fin & 3)) return 1;
   if (g_options[DSW_OPT_NO_TMA].load(std::memory_order_relaxed) != 0) return 1;
-  int pp = 256 / Fout;
+  int pp = 256 / ((Fout + 63) / 64 * 64);
   while (pp > 1 && Kb % pp) pp >>= 1;
   return pp;
 }
@@ -785,7 +786,7 @@ static int wgrad_span_planes(int32_t Kb, int32_t Fin, int32_t Fout) {
 static void wgrad_tc_geometry(int64_t N, int32_t Ka, int32_t Kb, int32_t Fin, int32_t Fout, int& BN, int& ntiles,
                               int& mtiles, int& nsplit, int& kb_per_split) {
   const int pp = wgrad_span_planes(Kb, Fin, Fout);
-  BN = pp > 1 ? pp * Fout : std::min(256, (Fout + 15) / 16 * 16);
+  BN = pp > 1 ? pp * ((Fout + 63) / 64 * 64) : std::min(256, (Fout + 15) / 16 * 16);
   ntiles = pp > 1 ? Kb / pp : Kb * ((Fout + BN - 1) / BN);
   const int ftiles = (Fin + 63) / 64;
   mtiles = (Ka * ftiles + 1) / 2;
