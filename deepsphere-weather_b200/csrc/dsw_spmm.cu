@@ -705,6 +705,10 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
       P.n_items = a.B * P.n_slabs;
       n_teams = std::min(n_teams, P.n_items);
       if (g_options[DSW_OPT_DEBUG].load(std::memory_order_relaxed) == 3) n_teams = std::min(n_teams, 2);
+      {
+        const int64_t cap = g_options[DSW_OPT_HOP_TEAMS].load(std::memory_order_relaxed);
+        if (cap > 0) n_teams = std::min<int>(n_teams, (int)cap);
+      }
       P.n_teams = n_teams;
       P.debug_skip = (int)g_options[DSW_OPT_DEBUG].load(std::memory_order_relaxed);
       // items per CTA: a few per team to amortise the staged panels, while keeping >= ~3 waves of CTAs

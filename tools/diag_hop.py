@@ -54,6 +54,10 @@ def main():
             lib.dsw_set_option(OPT_ROWS, rows)
             extra += f"  rows+{rows}={timed(lambda: F_.cheb_terms(x, plan, K), flush):7.1f}"
         lib.dsw_set_option(OPT_ROWS, 0)
+        for teams in (3, 4):
+            lib.dsw_set_option(13, teams)
+            extra += f"  teams{teams}={timed(lambda: F_.cheb_terms(x, plan, K), flush):7.1f}"
+        lib.dsw_set_option(13, 0)
         lib.dsw_set_option(11, 8)
         extra += f"  8lanes={timed(lambda: F_.cheb_terms(x, plan, K), flush):7.1f}"
         lib.dsw_set_option(11, 0)
