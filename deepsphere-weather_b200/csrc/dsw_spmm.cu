@@ -324,6 +324,7 @@ struct TeamHopPlan {
   int32_t n_teams;
   int32_t* cnt;           // per-tile claim counters of this launch (dynamic item scheduling) or null
   int32_t n_ctas;         // CTAs of this launch (the last one to leave zeroes the counters again)
+  int32_t prefetch_zg;    // 1 = L2-prefetch the next item's Z / G rows when its tile transfer is issued
   int32_t debug_skip;     // timing experiments only: 1 = skip staging, 2 = skip the entry loop
 };
 
@@ -368,6 +369,24 @@ __device__ __forceinline__ void fma_step(float4 (&acc)[4][NJ], const float4& w, 
     fma4(acc[1][j], w.y, x[j]);
     fma4(acc[2][j], w.z, x[j]);
     fma4(acc[3][j], w.w, x[j]);
+  }
+}
+
+// L2 prefetch of the Z / G rows of one work item (kept out of line so that it does not disturb the
+// register allocation of the entry loop).
+__device__ __noinline__ void hop_prefetch_zg(const float* z, int64_t z_sV, const float* g, int64_t g_sV, int rows, bool two_lines,
+                                             int tt, int team_threads) {
+  for (int r = tt; r < rows; r += team_threads) {
+    if (z != nullptr) {
+      const float* p = z + r * z_sV;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+      if (two_lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 32));
+    }
+    if (g != nullptr) {
+      const float* p = g + r * g_sV;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+      if (two_lines) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 32));
+    }
   }
 }
 
@@ -465,6 +484,14 @@ __global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
           const uint32_t meta = s_meta[i];
           tma_load_3d(xs_u32 + (meta >> 8) * 256u, &maps.m[meta & 7u], slab * 64, s_row[i], b, bar);
         }
+      }
+      // pull the item's Z / G rows (read at the top of the item, straight into the accumulators) towards
+      // L2 now, while the current item's stores and the tile transfer are in flight
+      if (P.prefetch_zg && (a.Z != nullptr || a.G != nullptr)) {
+        const int64_t row0 = (int64_t)blk0 * 4;
+        const int rows = (int)min((int64_t)(4 * DSW_TILE_BLOCKS), (int64_t)P.n_rows - row0);
+        hop_prefetch_zg(a.Z ? a.Z + b * a.z_sB + row0 * a.z_sV + slab * 64 : nullptr, a.z_sV,
+                        a.G ? a.G + b * a.g_sB + row0 * a.g_sV + slab * 64 : nullptr, a.g_sV, rows, slab_f > 32, tt, TEAM_THREADS);
       }
     } else {
       const float* xb = a.X + (int64_t)b * a.x_sB + slab * 64;
@@ -711,6 +738,7 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
       }
       P.n_teams = n_teams;
       P.debug_skip = (int)g_options[DSW_OPT_DEBUG].load(std::memory_order_relaxed);
+      P.prefetch_zg = g_options[DSW_OPT_HOP_PREFETCH].load(std::memory_order_relaxed) == 2 ? 0 : 1;
       // items per CTA: a few per team to amortise the staged panels, while keeping >= ~3 waves of CTAs
       int ipc = n_teams;
       while (ipc < 4 * n_teams && ipc * 2 <= P.n_items && (int64_t)rb.n_tiles * ceil_div(P.n_items, ipc * 2) >= 148 * 3)

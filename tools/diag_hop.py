@@ -45,12 +45,12 @@ def main():
         x = torch.randn(B, V, F, device=dev)
         K = 4
         row = []
-        for ipc in [0, 12, 24]:
+        for ipc in [0]:
             lib.dsw_set_option(OPT_IPC, ipc)
             row.append((ipc, timed(lambda: F_.cheb_terms(x, plan, K), flush)))
         lib.dsw_set_option(OPT_IPC, 0)
         extra = ""
-        for rows in (1, 3):
+        for rows in ():
             lib.dsw_set_option(OPT_ROWS, rows)
             extra += f"  rows+{rows}={timed(lambda: F_.cheb_terms(x, plan, K), flush):7.1f}"
         lib.dsw_set_option(OPT_ROWS, 0)
@@ -58,6 +58,9 @@ def main():
             lib.dsw_set_option(13, teams)
             extra += f"  teams{teams}={timed(lambda: F_.cheb_terms(x, plan, K), flush):7.1f}"
         lib.dsw_set_option(13, 0)
+        lib.dsw_set_option(14, 2)
+        extra += f"  no-prefetch={timed(lambda: F_.cheb_terms(x, plan, K), flush):7.1f}"
+        lib.dsw_set_option(14, 0)
         lib.dsw_set_option(11, 8)
         extra += f"  8lanes={timed(lambda: F_.cheb_terms(x, plan, K), flush):7.1f}"
         lib.dsw_set_option(11, 0)
