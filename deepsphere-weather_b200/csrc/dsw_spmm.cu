@@ -325,6 +325,7 @@ struct TeamHopPlan {
   int32_t* cnt;           // per-tile claim counters of this launch (dynamic item scheduling) or null
   int32_t n_ctas;         // CTAs of this launch (the last one to leave zeroes the counters again)
   int32_t prefetch_zg;    // 1 = L2-prefetch the next item's Z / G rows when its tile transfer is issued
+  int32_t pdl;            // 1 = launched with programmatic stream serialisation: the prologue may overlap the previous kernel
   int32_t debug_skip;     // timing experiments only: 1 = skip staging, 2 = skip the entry loop
 };
 
@@ -405,6 +406,9 @@ __global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
   const int len = __ldg(P.tp_ptr + tile + 1) - t0;
   const int r0 = __ldg(P.tile_ptr + tile);
   const int nrows = __ldg(P.tile_ptr + tile + 1) - r0;
+  // Programmatic dependent launch: the next kernel of the stream may start its CTAs (plan staging only) as
+  // soon as every CTA of this grid has got this far, i.e. while our last wave is still computing.
+  if (P.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // shared memory: [staged rows: n_teams x cap_rows x 256 B | weights | offsets | source-row ids]
   const size_t xbuf_bytes = (size_t)P.cap_rows * 256;
@@ -515,7 +519,7 @@ __global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
     team_sync<TEAM_THREADS>(team);
     item = s_claim[2 * team];
   }
-  if (TMA && team < P.n_teams && item < item_end) stage(item);
+  if (TMA && !P.pdl && team < P.n_teams && item < item_end) stage(item);
 
   // ---- prologue, part 2: the entry-major weight / offset panels ----
   {
@@ -530,6 +534,11 @@ __global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
   __syncthreads();
 
   if (team >= P.n_teams) return;
+  if (P.pdl) {
+    // everything above read only the plan; the operands may still be being written by the previous kernel
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (TMA && item < item_end) stage(item);
+  }
   const int slot = tt / LPR, lq = tt % LPR, par = slot & 1;
   const int blk = blk0 + slot;
   const bool active = blk < P.n_blocks;
@@ -775,11 +784,22 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
         }
       }
       const bool lpr8 = g_options[DSW_OPT_HOP_LPR].load(std::memory_order_relaxed) == 8;
+      P.pdl = g_options[DSW_OPT_NO_PDL].load(std::memory_order_relaxed) == 0 ? 1 : 0;
       auto launch = [&](auto kern, int threads, int slot) -> int {
         static std::atomic<bool> attr_done[4] = {{false}, {false}, {false}, {false}};
         if (!attr_done[slot].exchange(true))
           DSW_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        kern<<<grid, threads, smem, st>>>(P, a, maps);
+        if (P.pdl) {
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = grid, cfg.blockDim = dim3(threads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+          cudaLaunchAttribute attr[1];
+          attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+          attr[0].val.programmaticStreamSerializationAllowed = 1;
+          cfg.attrs = attr, cfg.numAttrs = 1;
+          DSW_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, P, a, maps));
+        } else {
+          kern<<<grid, threads, smem, st>>>(P, a, maps);
+        }
         return check_launch();
       };
       if (tma) return lpr8 ? launch(hop_team_kernel<true, 8>, DSW_TILE_BLOCKS * 8 * MAX_TEAMS, 0)

@@ -61,6 +61,9 @@ def main():
         lib.dsw_set_option(14, 2)
         extra += f"  no-prefetch={timed(lambda: F_.cheb_terms(x, plan, K), flush):7.1f}"
         lib.dsw_set_option(14, 0)
+        lib.dsw_set_option(15, 1)
+        extra += f"  no-PDL={timed(lambda: F_.cheb_terms(x, plan, K), flush):7.1f}"
+        lib.dsw_set_option(15, 0)
         lib.dsw_set_option(11, 8)
         extra += f"  8lanes={timed(lambda: F_.cheb_terms(x, plan, K), flush):7.1f}"
         lib.dsw_set_option(11, 0)
