@@ -18,6 +18,7 @@ constexpr int EW_BLOCKS = 148 * 4;  // partial sums of the backward reduction
 __global__ void __launch_bounds__(EW_THREADS) rezero_fwd_kernel(const float* __restrict__ a, const float* __restrict__ s,
                                                                 const float* __restrict__ w, float* __restrict__ y,
                                                                 int64_t n4, int64_t n) {
+  pdl_trigger();
   const float ww = __ldg(w);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(EW_THREADS) rezero_bwd_kernel(const float* __r
 __global__ void __launch_bounds__(EW_THREADS) rezero_reduce_kernel(const float* __restrict__ partial, int32_t np,
                                                                    float* __restrict__ dw) {
   __shared__ double red[EW_THREADS];
+  pdl_trigger();
   double s = 0.0;
   for (int i = threadIdx.x; i < np; i += EW_THREADS) s += (double)partial[i];
   red[threadIdx.x] = s;

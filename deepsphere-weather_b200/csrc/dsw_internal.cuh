@@ -204,3 +204,26 @@ __device__ __forceinline__ void split_quad(const float4& v, uint2& hi, uint2& lo
 }
 }  // namespace dsw
 #endif
+
+#ifdef __CUDACC__
+namespace dsw {
+// Programmatic dependent launch (PDL).  A kernel that calls pdl_trigger() lets the NEXT kernel of the stream —
+// if that one was launched with launch_pdl() — start its CTAs while this grid is still finishing; such a
+// dependent kernel reads only launch-invariant data (plans, barriers, TMEM) until it calls pdl_wait(), which
+// returns once every earlier kernel has completed and its writes are visible.  Both are no-ops otherwise.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <class Kern, class... Args>
+inline cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+inline bool pdl_enabled() { return g_options[DSW_OPT_NO_PDL].load(std::memory_order_relaxed) == 0; }
+}  // namespace dsw
+#endif

@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradArgs a, int32_t ft
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int32_t nsplit, int64_t n_w,
                                                            int32_t Fout, float* __restrict__ dW, float* __restrict__ dbias) {
   __shared__ float red[8][32];
+  pdl_trigger();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t total = n_w + Fout;
   const int64_t i = (int64_t)blockIdx.x * 32 + lane;

@@ -146,6 +146,7 @@ struct TcArgs {
 // B preparation: split weights into bf16 hi/lo and write shared-memory images
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) mix_tc_prep_kernel(TcArgs P, uint8_t* __restrict__ out, int32_t n_tiles) {
+  pdl_trigger();
   const MixArgs& a = P.m;
   const int64_t chunks_per_img = (int64_t)P.BN * 8;  // 16-byte chunks
   const int64_t total = (int64_t)n_tiles * a.P * P.nkb * chunks_per_img;
@@ -471,6 +472,7 @@ __device__ __forceinline__ int epi_off(int row, int chunk) { return row * EPI_PI
 
 __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_constant__ TmaArgs Q) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
   const TcArgs& P = Q.tc;
   const MixArgs& a = P.m;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -513,6 +515,7 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_wait();  // barriers and TMEM are set up; the operands may still be being written by the previous kernel
 
   const int total_kb = a.P * P.nkb;
   const int last_ksteps = (a.Ka - (P.nkb - 1) * BKB + 15) / 16;  // K-steps (of 16) in a plane's last block
@@ -823,7 +826,7 @@ int launch_mix_tc_ws(const MixArgs& a, void* prep, size_t prep_bytes, bool do_pr
       static std::atomic<bool> attr_tma{false};
       if (!attr_tma.exchange(true))
         DSW_CUDA_TRY(cudaFuncSetAttribute(tc::mix_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      tc::mix_tma_kernel<<<grid, tc::THREADS2, smem, st>>>(Q);
+      DSW_CUDA_TRY(launch_pdl(tc::mix_tma_kernel, grid, dim3(tc::THREADS2), smem, st, pdl_enabled(), Q));
       return check_launch();
     }
   }

@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(256) hop_csr_kernel(const int32_t* __restrict_
                                                       const int32_t* __restrict__ col,
                                                       const float* __restrict__ val, int32_t n_rows,
                                                       int32_t lpr_log2, HopArgs a) {
+  pdl_trigger();
   const int lpr = 1 << lpr_log2;
   const int lane = threadIdx.x & (lpr - 1);
   const int row = blockIdx.x * (blockDim.x >> lpr_log2) + (threadIdx.x >> lpr_log2);
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
   const int nrows = __ldg(P.tile_ptr + tile + 1) - r0;
   // Programmatic dependent launch: the next kernel of the stream may start its CTAs (plan staging only) as
   // soon as every CTA of this grid has got this far, i.e. while our last wave is still computing.
-  if (P.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (P.pdl) pdl_trigger();
 
   // shared memory: [staged rows: n_teams x cap_rows x 256 B | weights | offsets | source-row ids]
   const size_t xbuf_bytes = (size_t)P.cap_rows * 256;
@@ -536,7 +537,7 @@ __global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
   if (team >= P.n_teams) return;
   if (P.pdl) {
     // everything above read only the plan; the operands may still be being written by the previous kernel
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    pdl_wait();
     if (TMA && item < item_end) stage(item);
   }
   const int slot = tt / LPR, lq = tt % LPR, par = slot & 1;

@@ -457,6 +457,7 @@ __device__ unsigned long long g_wgrad_prof[8];
 template <bool PAIR>
 __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_constant__ WtmaArgs Q) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
   __shared__ float bias_acc[256];
   const WtcArgs& P = Q.c;
   const WgradArgs& a = P.w;
@@ -515,6 +516,7 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
   if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anyone arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_wait();  // barriers and TMEM are set up; the operands may still be being written by the previous kernel
 
   if (warp < 8) {
     // ================= converters =================
@@ -855,7 +857,8 @@ int launch_wgrad_tc(const WgradArgs& a, size_t partial_bytes, cudaStream_t st) {
       }
       if (!attr_tma[0].exchange(true))
         DSW_CUDA_TRY(cudaFuncSetAttribute(wtc::wgrad_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-      wtc::wgrad_tma_kernel<false><<<grid, wtc::T_THREADS, wtc::tma_smem_bytes_for(P.nb), st>>>(Q);
+      DSW_CUDA_TRY(launch_pdl(wtc::wgrad_tma_kernel<false>, grid, dim3(wtc::T_THREADS), wtc::tma_smem_bytes_for(P.nb), st,
+                              pdl_enabled(), Q));
       return check_launch();
     }
   }
