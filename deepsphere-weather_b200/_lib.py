@@ -96,6 +96,11 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    # tuning switches for A/B runs: DSW_OPTIONS="key=value,key=value" (keys: DSW_OPT_* of include/dsw.h)
+    for kv in filter(None, os.environ.get("DSW_OPTIONS", "").split(",")):
+        k, v = kv.split("=")
+        if lib.dsw_set_option(int(k), int(v)) != 0:
+            raise DswError(f"DSW_OPTIONS: bad option {kv!r}")
     _lib = lib
     return lib
 

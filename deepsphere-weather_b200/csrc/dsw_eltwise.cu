@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(EW_THREADS) rezero_fwd_kernel(const float* __r
                                                                 const float* __restrict__ w, float* __restrict__ y,
                                                                 int64_t n4, int64_t n) {
   pdl_trigger();
+  pdl_wait();
   const float ww = __ldg(w);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -36,6 +37,8 @@ __global__ void __launch_bounds__(EW_THREADS) rezero_bwd_kernel(const float* __r
                                                                 const float* __restrict__ w, float* __restrict__ da,
                                                                 float* __restrict__ partial, int64_t n4, int64_t n) {
   __shared__ float red[EW_THREADS / 32];
+  pdl_trigger();
+  pdl_wait();
   const float ww = __ldg(w);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -70,6 +73,7 @@ __global__ void __launch_bounds__(EW_THREADS) rezero_reduce_kernel(const float* 
                                                                    float* __restrict__ dw) {
   __shared__ double red[EW_THREADS];
   pdl_trigger();
+  pdl_wait();
   double s = 0.0;
   for (int i = threadIdx.x; i < np; i += EW_THREADS) s += (double)partial[i];
   red[threadIdx.x] = s;
@@ -96,7 +100,8 @@ int dsw_rezero_fwd(const float* conv_out, const float* skip, const float* w, flo
   const bool v4 = al16(conv_out) && al16(skip) && al16(y);
   const int64_t n4 = v4 ? n / 4 : 0;
   const int blocks = (int)std::min<int64_t>(EW_BLOCKS * 4, ceil_div64(std::max<int64_t>(n4, n - n4 * 4), EW_THREADS));
-  rezero_fwd_kernel<<<std::max(blocks, 1), EW_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(conv_out, skip, w, y, n4, n);
+  DSW_CUDA_TRY(launch_pdl(rezero_fwd_kernel, dim3(std::max(blocks, 1)), dim3(EW_THREADS), 0, static_cast<cudaStream_t>(stream), pdl_enabled(),
+                          conv_out, skip, w, y, n4, n));
   return check_launch();
 }
 
@@ -108,10 +113,10 @@ int dsw_rezero_bwd(const float* g, const float* conv_out, const float* w, float*
   const bool v4 = al16(g) && (!conv_out || al16(conv_out)) && (!d_conv_out || al16(d_conv_out));
   const int64_t n4 = v4 ? n / 4 : 0;
   float* partial = d_w ? static_cast<float*>(workspace) : nullptr;
-  rezero_bwd_kernel<<<EW_BLOCKS, EW_THREADS, 0, st>>>(g, conv_out, w, d_conv_out, partial, n4, n);
+  DSW_CUDA_TRY(launch_pdl(rezero_bwd_kernel, dim3(EW_BLOCKS), dim3(EW_THREADS), 0, st, pdl_enabled(), g, conv_out, w, d_conv_out, partial, n4, n));
   DSW_TRY(check_launch());
   if (d_w) {
-    rezero_reduce_kernel<<<1, EW_THREADS, 0, st>>>(partial, EW_BLOCKS, d_w);
+    DSW_CUDA_TRY(launch_pdl(rezero_reduce_kernel, dim3(1), dim3(EW_THREADS), 0, st, pdl_enabled(), (const float*)partial, (int32_t)EW_BLOCKS, d_w));
     DSW_TRY(check_launch());
   }
   return DSW_OK;

@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
                                                            int32_t Fout, float* __restrict__ dW, float* __restrict__ dbias) {
   __shared__ float red[8][32];
   pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t total = n_w + Fout;
   const int64_t i = (int64_t)blockIdx.x * 32 + lane;
@@ -261,7 +262,8 @@ int launch_wgrad_reduce(const float* partial, int32_t nsplit, int32_t K, int32_t
                         float* dbias, cudaStream_t st) {
   const int64_t n_w = (int64_t)K * Fin * Fout;
   const int64_t total = n_w + Fout;
-  wgrad_reduce_kernel<<<(unsigned)ceil_div64(total, 32), 256, 0, st>>>(partial, nsplit, n_w, Fout, dW, dbias);
+  DSW_CUDA_TRY(launch_pdl(wgrad_reduce_kernel, dim3((unsigned)ceil_div64(total, 32)), dim3(256), 0, st, pdl_enabled(), partial, nsplit, n_w, Fout, dW,
+                          dbias));
   return check_launch();
 }
 

@@ -147,6 +147,7 @@ struct TcArgs {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) mix_tc_prep_kernel(TcArgs P, uint8_t* __restrict__ out, int32_t n_tiles) {
   pdl_trigger();
+  pdl_wait();
   const MixArgs& a = P.m;
   const int64_t chunks_per_img = (int64_t)P.BN * 8;  // 16-byte chunks
   const int64_t total = (int64_t)n_tiles * a.P * P.nkb * chunks_per_img;
@@ -799,7 +800,8 @@ int launch_mix_tc_ws(const MixArgs& a, void* prep, size_t prep_bytes, bool do_pr
 
   if (do_prep) {
     const int64_t chunks = (int64_t)n_tiles * a.P * P.nkb * P.BN * 8;
-    tc::mix_tc_prep_kernel<<<(unsigned)ceil_div64(chunks, 256), 256, 0, st>>>(P, static_cast<uint8_t*>(prep), n_tiles);
+    DSW_CUDA_TRY(launch_pdl(tc::mix_tc_prep_kernel, dim3((unsigned)ceil_div64(chunks, 256)), dim3(256), 0, st, pdl_enabled(), P,
+                            static_cast<uint8_t*>(prep), (int32_t)n_tiles));
     DSW_TRY(check_launch());
   }
 

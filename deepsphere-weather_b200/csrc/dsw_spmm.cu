@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(256) hop_csr_kernel(const int32_t* __restrict_
                                                       const float* __restrict__ val, int32_t n_rows,
                                                       int32_t lpr_log2, HopArgs a) {
   pdl_trigger();
+  pdl_wait();
   const int lpr = 1 << lpr_log2;
   const int lane = threadIdx.x & (lpr - 1);
   const int row = blockIdx.x * (blockDim.x >> lpr_log2) + (threadIdx.x >> lpr_log2);
@@ -851,9 +852,11 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
   const int rows_per_cta = 256 >> lpr_log2;
   dim3 grid(ceil_div(A.n_rows, rows_per_cta), a.B);
   if (v4)
-    hop_csr_kernel<4><<<grid, 256, 0, st>>>(A.rowptr, A.col, A.val, A.n_rows, lpr_log2, a);
+    DSW_CUDA_TRY(launch_pdl(hop_csr_kernel<4>, grid, dim3(256), 0, st, pdl_enabled(), (const int32_t*)A.rowptr, (const int32_t*)A.col,
+                            (const float*)A.val, (int32_t)A.n_rows, (int32_t)lpr_log2, a));
   else
-    hop_csr_kernel<1><<<grid, 256, 0, st>>>(A.rowptr, A.col, A.val, A.n_rows, lpr_log2, a);
+    DSW_CUDA_TRY(launch_pdl(hop_csr_kernel<1>, grid, dim3(256), 0, st, pdl_enabled(), (const int32_t*)A.rowptr, (const int32_t*)A.col,
+                            (const float*)A.val, (int32_t)A.n_rows, (int32_t)lpr_log2, a));
   return check_launch();
 }
 
