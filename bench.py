@@ -198,10 +198,10 @@ def time_kernel_rooflines(device, hbm_gbs, bf16_tflops):
     per_launch_bytes = alg_bytes / n_launch
     achieved = alg_bytes / t / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the three hop launches in
-    # profiles/r01j_hop_team_kernel_ncu.txt (one `ncu --set full` capture of this same call):
-    # (463.2 + 361.0) + (867.4 + 373.5) + (867.2 + 374.4) MB over 3 launches.  Each unfused hop moves
+    # profiles/r01k_hop_team_kernel_ncu.txt (one `ncu --set full` capture of this same call):
+    # (462.4 + 363.9) + (867.3 + 376.2) + (867.3 + 374.9) MB over 3 launches.  Each unfused hop moves
     # ~3 planes (gather source, k-2 term, output) where the K-plane accounting counts 4/3.
-    ncu_traffic_bytes_per_launch = 1102.2e6
+    ncu_traffic_bytes_per_launch = 1104.0e6
     out["roofline"] = {
         "kernel": "hop_team_kernel (Chebyshev SpMM hop), dsw_cheb_terms nside64 B32 F64 K4", "bound": "hbm",
         "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
