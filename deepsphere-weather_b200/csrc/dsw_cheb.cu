@@ -114,7 +114,7 @@ static int run_terms(const dsw_csr& A, const dsw_rb& rb, const float* x, int64_t
 // Clenshaw recurrence under operator A, in place on the K planes G ([K][plane], F channels):
 //   b_{K-1} = G_{K-1};  b_k = G_k + 2 A b_{k+1} - b_{k+2}  (k = K-2 .. 1);  out = G_0 + A b_1 - b_2
 static int run_clenshaw(const dsw_csr& A, const dsw_rb& rb, float* G, int64_t plane, float* out, int32_t Bc, int32_t F,
-                        int32_t K, cudaStream_t st) {
+                        int32_t K, cudaStream_t st, int32_t act = 0) {
   const int64_t V = A.n_rows, sB = V * F, sV = F;
   for (int k = K - 2; k >= 0; --k) {
     HopArgs a;
@@ -124,6 +124,7 @@ static int run_clenshaw(const dsw_csr& A, const dsw_rb& rb, float* G, int64_t pl
     a.G = G + k * plane, a.g_sB = sB, a.g_sV = sV;
     a.alpha = (k == 0) ? 1.f : 2.f;
     a.O = (k == 0) ? out : G + k * plane, a.o_sB = sB, a.o_sV = sV;
+    a.act = (k == 0) ? act : 0;  // the activation follows the last hop
     DSW_TRY(launch_hop(A, rb, a, st));
   }
   return DSW_OK;
@@ -214,7 +215,6 @@ int dsw_cheb_fwd(const dsw_plan* lap, const float* x, int64_t x_sB, int64_t x_sV
   }
 
   // CLENSHAW: G_k = x W_k (+ bias on plane 0), then the recurrence with L on Fout channels
-  if (act != 0) return DSW_ERR_UNSUPPORTED;  // the activation would have to follow the last hop
   float* G = static_cast<float*>(workspace);
   const size_t g_bytes = align_up((size_t)K * Bc * V * Fout * sizeof(float), 256);
   void* prep = static_cast<char*>(workspace) + g_bytes;
@@ -229,7 +229,7 @@ int dsw_cheb_fwd(const dsw_plan* lap, const float* x, int64_t x_sB, int64_t x_sV
     m.bias = bias, m.bias_n = Fout;  // only plane 0 (c < Fout) carries the bias
     m.C = G, m.sCp = plane, m.ldc = Fout, m.Cw = Fout, m.Nc = K * Fout, m.act = 0;
     DSW_TRY(launch_mix(m, prep, prep_bytes, b0 == 0, st));
-    DSW_TRY(run_clenshaw(lap->fwd, lap->fwd_rb, G, plane, y + (int64_t)b0 * V * Fout, Bc, Fout, K, st));
+    DSW_TRY(run_clenshaw(lap->fwd, lap->fwd_rb, G, plane, y + (int64_t)b0 * V * Fout, Bc, Fout, K, st, act));
   }
   return DSW_OK;
 }

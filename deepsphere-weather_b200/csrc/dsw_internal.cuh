@@ -122,6 +122,7 @@ struct HopArgs {
   int64_t o_sB = 0, o_sV = 0;
   float alpha = 1.f, beta = 0.f;
   int32_t B = 0, F = 0;
+  int32_t act = 0;           // 1 = ReLU on the result (the last hop of a fused conv + activation)
 };
 int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_t st);
 

@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(512) hop_rb_kernel(const int32_t* __restrict__
       const float4 g = ldg4(a.G + b * a.g_sB + row * a.g_sV + c4 * 4);
       o.x += g.x, o.y += g.y, o.z += g.z, o.w += g.w;
     }
+    if (a.act) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
     *reinterpret_cast<float4*>(a.O + b * a.o_sB + row * a.o_sV + c4 * 4) = o;
   }
 }
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(256) hop_csr_kernel(const int32_t* __restrict_
       float o = a.alpha * acc[i];
       if (a.Z) o = fmaf(a.beta, __ldg(a.Z + b * a.z_sB + row * a.z_sV + f + i), o);
       if (a.G) o += __ldg(a.G + b * a.g_sB + row * a.g_sV + f + i);
-      acc[i] = o;
+      acc[i] = a.act ? fmaxf(o, 0.f) : o;
     }
     float* op = a.O + b * a.o_sB + row * a.o_sV + f;
     if constexpr (VEC == 4) {
@@ -279,6 +280,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) hop_tile_kernel(const int32_t
           const float4 g = ldg4(a.G + b * a.g_sB + row * a.g_sV + col);
           o.x += g.x, o.y += g.y, o.z += g.z, o.w += g.w;
         }
+        if (a.act) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
         *reinterpret_cast<float4*>(a.O + b * a.o_sB + row * a.o_sV + col) = o;
       }
     }
@@ -678,8 +680,9 @@ __global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
         for (int j = 0; j < NJ; ++j) {
           if (ch[j] >= slab_f) continue;
           const int64_t col = (int64_t)slab * 64 + ch[j];
-          *reinterpret_cast<float4*>(a.O + b * a.o_sB + row * a.o_sV + col) =
-              make_float4(a.alpha * acc[r][j].x, a.alpha * acc[r][j].y, a.alpha * acc[r][j].z, a.alpha * acc[r][j].w);
+          float4 o = make_float4(a.alpha * acc[r][j].x, a.alpha * acc[r][j].y, a.alpha * acc[r][j].z, a.alpha * acc[r][j].w);
+          if (a.act) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+          *reinterpret_cast<float4*>(a.O + b * a.o_sB + row * a.o_sV + col) = o;
         }
       }
     }

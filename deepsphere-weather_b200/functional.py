@@ -127,7 +127,7 @@ def plan_for(coo: torch.Tensor) -> SparsePlan:
 
 class ChebConvFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, plan: SparsePlan):
+    def forward(ctx, x, weight, bias, plan: SparsePlan, act: int = 0):
         _require_cuda_f32(x, "inputs")
         _require_cuda_f32(weight, "weight")
         B, V, Fin = x.shape
@@ -152,7 +152,7 @@ class ChebConvFunction(torch.autograd.Function):
         with torch.cuda.device(x.device):
             rc = lib.dsw_cheb_fwd(
                 plan.handle, x.data_ptr(), x.stride(0), x.stride(1), w.data_ptr(), bptr, y.data_ptr(),
-                B, Fin, Fout, K, 0, ws.data_ptr(), ws.numel(), _stream_ptr(x.device),
+                B, Fin, Fout, K, int(act), ws.data_ptr(), ws.numel(), _stream_ptr(x.device),
             )
         _lib.check(rc, "dsw_cheb_fwd")
         # Only x and W are saved: callers modify our output in place (`x_out *= rezero_weight`,
@@ -162,16 +162,23 @@ class ChebConvFunction(torch.autograd.Function):
         keep = (_SAVE_TERMS and K > 1 and lib.dsw_get_option(_OPT_L2_CHUNK) <= 1
                 and lib.dsw_cheb_fwd_algo(Fin, Fout, K) == 1 and lib.dsw_cheb_bwd_algo(Fin, Fout, K) == 2
                 and (ctx.needs_input_grad[1] or (bias is not None and ctx.needs_input_grad[2])))
-        ctx.save_for_backward(x, w, *([ws] if keep else []))
+        # act = 1 (ReLU fused into the last kernel of the forward): the backward masks dy with the sign of the
+        # output, which is therefore saved — such a layer's output must not be modified in place by the caller
+        # (the reference applies its activation out of place, my_models_graph.py:113).
+        ctx.save_for_backward(x, w, *([ws] if keep else []), *([y] if act else []))
         ctx.plan = plan
         ctx.has_bias = bias is not None
+        ctx.act = int(act)
+        ctx.keep = bool(keep)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
         x, w, *saved = ctx.saved_tensors
-        terms_ptr = saved[0].data_ptr() if saved else None
+        if ctx.act:
+            dy = torch.ops.aten.threshold_backward(dy, saved.pop(), 0.0)  # ReLU mask (what F.relu's backward does)
+        terms_ptr = saved[0].data_ptr() if ctx.keep else None
         plan = ctx.plan
         lib = _lib.load()
         B, V, Fin = x.shape
@@ -180,7 +187,7 @@ class ChebConvFunction(torch.autograd.Function):
         need_dx = ctx.needs_input_grad[0]
         need_dw = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
         if not (need_dx or need_dw):
-            return None, None, None, None
+            return None, None, None, None, None
         dx = torch.empty((B, V, Fin), dtype=torch.float32, device=x.device) if need_dx else None
         dw = torch.empty_like(w) if need_dw else None
         db = torch.empty(Fout, dtype=torch.float32, device=x.device) if (need_dw and ctx.has_bias) else None
@@ -194,11 +201,11 @@ class ChebConvFunction(torch.autograd.Function):
                 _stream_ptr(x.device),
             )
         _lib.check(rc, "dsw_cheb_bwd")
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
-def cheb_conv(x, weight, bias, plan: SparsePlan):
-    return ChebConvFunction.apply(x, weight, bias, plan)
+def cheb_conv(x, weight, bias, plan: SparsePlan, act: int = 0):
+    return ChebConvFunction.apply(x, weight, bias, plan, act)
 
 
 def cheb_terms(x: torch.Tensor, plan: SparsePlan, K: int) -> torch.Tensor:

@@ -48,7 +48,7 @@ def _pad4(n: int) -> int:
     return (-n) % 4
 
 
-def _cheb_conv_padded(inputs, weight, bias, plan):
+def _cheb_conv_padded(inputs, weight, bias, plan, act=0):
     """Channel counts that are not multiples of 4 (21 input features, 2 outputs) would force the
     unaligned scalar kernels (no 16-byte rows, no TMA).  Zero-padding the channel dimension of the
     activations and of ``weight`` / ``bias`` is exact — padded inputs meet zero weights, padded outputs
@@ -56,11 +56,11 @@ def _cheb_conv_padded(inputs, weight, bias, plan):
     gradients back."""
     pin, pout = _pad4(inputs.shape[2]), _pad4(weight.shape[2])
     if inputs.shape[2] != weight.shape[0] or (pin == 0 and pout == 0):
-        return F_.cheb_conv(inputs, weight, bias, plan)  # (a shape mismatch raises the reference's error there)
+        return F_.cheb_conv(inputs, weight, bias, plan, act)  # (a shape mismatch raises the reference's error there)
     x = torch.nn.functional.pad(inputs, (0, pin)) if pin else inputs
     w = torch.nn.functional.pad(weight, (0, pout, 0, 0, 0, pin)) if (pin or pout) else weight
     b = torch.nn.functional.pad(bias, (0, pout)) if (bias is not None and pout) else bias
-    y = F_.cheb_conv(x, w, b, plan)
+    y = F_.cheb_conv(x, w, b, plan, act)
     return y[..., : weight.shape[2]] if pout else y
 
 
@@ -124,13 +124,21 @@ class ConvCheb(torch.nn.Module):
             self.in_channels, self.out_channels, self.kernel_size, self.bias is not None
         )
 
-    def forward(self, inputs):
+    # activations ``forward(..., activation=)`` can fuse into the convolution's last kernel
+    fused_activations = ("relu",)
+
+    def forward(self, inputs, activation=None):
+        """``forward(inputs)`` is the reference's signature; ``activation="relu"`` (an extension used by
+        ``models.ConvBlock``) applies the ReLU inside the convolution's last kernel instead of in a
+        separate element-wise pass."""
+        if activation not in (None,) + self.fused_activations:
+            raise ValueError(f"activation {activation!r} cannot be fused; apply it to the output instead")
         if self._conv is not conv_cheb:  # user-supplied convolution: honour the reference contract
             out = self._conv(self.laplacian, inputs, self.weight)
             if self.bias is not None:
                 out += self.bias
-            return out
-        return _cheb_conv_padded(inputs, self.weight, self.bias, F_.plan_for(self.laplacian))
+            return torch.relu(out) if activation == "relu" else out
+        return _cheb_conv_padded(inputs, self.weight, self.bias, F_.plan_for(self.laplacian), 1 if activation == "relu" else 0)
 
 
 class NodeLinear(torch.nn.Linear):

@@ -55,11 +55,17 @@ class ConvBlock(torch.nn.Module):
         self.norm = batch_norm
         self.act = activation
         self.act_fun = getattr(F, activation_fun)
+        # ReLU directly after the convolution: let the convolution apply it in its last kernel
+        self._fused_act = (activation_fun if activation and activation_fun in getattr(self.conv, "fused_activations", ())
+                           and not (batch_norm and batch_norm_before_activation) else None)
 
     def _bn(self, x):
         return self.bn(x.permute(0, 2, 1)).permute(0, 2, 1)
 
     def forward(self, x):
+        if self._fused_act is not None:
+            x = self.conv(x, activation=self._fused_act)
+            return self._bn(x) if self.norm else x
         x = self.conv(x)
         if self.norm and self.bn_before_act:
             x = self._bn(x)

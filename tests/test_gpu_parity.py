@@ -554,6 +554,43 @@ def test_rezero_residual_matches_torch(shape, w0, dev):
     assert rel_err(y2, (wide[..., : shape[2]].cpu() * w + s).numpy()) < 1e-6
 
 
+@pytest.mark.parametrize("Fin,Fout", [(32, 96), (96, 32), (21, 64), (64, 2)])
+@pytest.mark.parametrize("fwd_algo", [1, 2], ids=["terms", "clenshaw"])
+def test_fused_relu_matches_separate_relu(Fin, Fout, fwd_algo, dev, lib, mix_mode):
+    """ConvCheb(..., activation="relu") (ReLU inside the last kernel of either evaluation order, mask of the
+    saved output in the backward) against the reference composition act(conv(x)) (my_models_graph.py:104-118)."""
+    from deepsphere_weather_b200 import graphs as G
+    from deepsphere_weather_b200 import layers as L
+
+    torch.manual_seed(9)
+    lap = G.healpix_laplacian(4)
+    K, B, V = 3, 3, lap.shape[0]
+    layer = L.ConvCheb(Fin, Fout, K, lap).to(dev)
+    with torch.no_grad():
+        layer.bias.normal_(0, 0.1)
+    x = torch.randn(B, V, Fin, device=dev)
+    dy = torch.randn(B, V, Fout, device=dev)
+    lib.dsw_set_option(4, fwd_algo)
+    try:
+        xa = x.clone().requires_grad_(True)
+        ya = torch.relu(layer(xa))
+        ya.backward(dy)
+        ga = [xa.grad.clone(), layer.weight.grad.clone(), layer.bias.grad.clone()]
+        layer.zero_grad(set_to_none=True)
+        xb = x.clone().requires_grad_(True)
+        yb = layer(xb, activation="relu")
+        yb.backward(dy)
+        gb = [xb.grad, layer.weight.grad, layer.bias.grad]
+    finally:
+        lib.dsw_set_option(4, 0)
+    assert torch.equal(ya, yb)
+    for p, q in zip(ga, gb):
+        # (the tcgen05 weight gradient sums its bias partial with shared-memory float atomics: last-bit noise)
+        assert rel_err(q, p) < 1e-6
+    with pytest.raises(ValueError):
+        layer(x, activation="tanh")
+
+
 def test_hops_replay_in_a_cuda_graph(dev):
     """The dynamically scheduled hop kernel keeps claim counters in the plan; they must be back to
     zero after every launch so that replays of a captured CUDA graph (same counter set every time)
