@@ -42,6 +42,7 @@ SIGNATURES = {
     "dsw_linear_workspace_bytes": (_sz, [_i32] * 4),
     "dsw_linear_fwd": (C.c_int, [_ptr, _i64, _i64, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _sz, _ptr]),
     "dsw_linear_bwd": (C.c_int, [_ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _sz, _ptr]),
+    "dsw_linear_rezero_fwd": (C.c_int, [_ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _sz, _ptr]),
     "dsw_rezero_fwd": (C.c_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
     "dsw_rezero_bwd_workspace_bytes": (_sz, []),
     "dsw_rezero_bwd": (C.c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _i64, _ptr]),

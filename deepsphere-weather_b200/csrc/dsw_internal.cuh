@@ -146,6 +146,10 @@ struct MixArgs {
   int32_t Nc = 0;   // total output columns
   int64_t N = 0;    // rows
   int32_t act = 0;
+  // optional addend (single-plane outputs only, Cw == Nc):  C[n][c] += r_scale[0] * R[n * ldr + c]
+  const float* R = nullptr;
+  int64_t ldr = 0;
+  const float* r_scale = nullptr;  // device scalar; null = 1
 };
 int launch_mix_simt(const MixArgs& a, cudaStream_t st);
 

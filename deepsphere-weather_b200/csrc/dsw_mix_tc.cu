@@ -424,6 +424,7 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tc_kernel(const __grid_consta
           for (int e = 0; e < 4; ++e) {
             v[e] = __uint_as_float(r[j + e]);
             if (a.bias && cg + e < a.bias_n) v[e] += __ldg(a.bias + cg + e);
+            if (a.R && cg + e < a.Nc) v[e] = fmaf(a.r_scale ? __ldg(a.r_scale) : 1.f, __ldg(a.R + n * a.ldr + cg + e), v[e]);
             if (a.act == 1) v[e] = fmaxf(v[e], 0.f);
           }
           if (vec_store && cg + 3 < a.Nc) {
@@ -673,7 +674,39 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
           const bool vec = vec_ok && (col + 3 < a.Nc) && (ccol + 3 < a.Cw);
           float* cbase = a.C + (int64_t)cp * a.sCp + ccol;
           const bool relu = a.act == 1;
-          if (vec) {
+          if (vec && a.R != nullptr) {
+            // same, plus the addend row segments (C += r_scale * R): their global loads are issued first
+            const float rs = a.r_scale ? __ldg(a.r_scale) : 1.f;
+            const bool r_vec = (a.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.R) & 15) == 0);
+            float* cp_row = cbase + (row0 + half) * a.ldc;
+            const float* r_row = a.R + (row0 + half) * a.ldr + col;
+            const int64_t step = 2 * (int64_t)a.ldc, rstep = 2 * a.ldr;
+            int64_t n = row0 + half;
+#pragma unroll
+            for (int i0 = 0; i0 < 16; i0 += 4) {
+              float4 rv[4], v[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (n + 2 * i < a.N) {
+                  const float* rp = r_row + i * rstep;
+                  rv[i] = r_vec ? __ldg(reinterpret_cast<const float4*>(rp)) : make_float4(__ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3));
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(stg + epi_off(2 * (i0 + i) + half, c4));
+#pragma unroll
+              for (int i = 0; i < 4; ++i, n += 2, cp_row += step) {
+                if (n >= a.N) continue;
+                float4 o = v[i];
+                o.x = fmaf(rs, rv[i].x, o.x + bv[0]), o.y = fmaf(rs, rv[i].y, o.y + bv[1]);
+                o.z = fmaf(rs, rv[i].z, o.z + bv[2]), o.w = fmaf(rs, rv[i].w, o.w + bv[3]);
+                if (relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+                *reinterpret_cast<float4*>(cp_row) = o;
+              }
+              r_row += 4 * rstep;
+            }
+          } else if (vec) {
             // two phases per 16 rows so that 8 shared-memory reads, then 8 row-segment stores, overlap
             float* cp_row = cbase + (row0 + half) * a.ldc;
             const int64_t step = 2 * (int64_t)a.ldc;
@@ -698,10 +731,11 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
               const int64_t n = row0 + rr + half;
               if (n >= a.N) continue;
               const float4 v = *reinterpret_cast<const float4*>(stg + epi_off(rr + half, c4));
-              const float ve[4] = {v.x + bv[0], v.y + bv[1], v.z + bv[2], v.w + bv[3]};
+              float ve[4] = {v.x + bv[0], v.y + bv[1], v.z + bv[2], v.w + bv[3]};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 if (col + e >= a.Nc) break;
+                if (a.R) ve[e] = fmaf(a.r_scale ? __ldg(a.r_scale) : 1.f, __ldg(a.R + n * a.ldr + col + e), ve[e]);
                 const int cpe = (col + e) / a.Cw, cce = (col + e) - cpe * a.Cw;
                 a.C[(int64_t)cpe * a.sCp + n * a.ldc + cce] = relu ? fmaxf(ve[e], 0.f) : ve[e];
               }

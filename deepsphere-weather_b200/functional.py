@@ -332,6 +332,71 @@ def rezero_residual(conv_out, skip, weight):
     return RezeroResidualFunction.apply(conv_out, skip, weight)
 
 
+class LinearRezeroFunction(torch.autograd.Function):
+    """The whole ResBlock tail when the skip connection is a Linear, in one launch:
+    ``y = x @ W^T + b + rezero_weight * conv_out`` (``dsw_linear_rezero_fwd``: the channel-mix epilogue adds the
+    scaled convolution branch).  Backward = ``dsw_linear_bwd`` with ``dy = g`` and ``dsw_rezero_bwd``."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, conv_out, rezero_weight):
+        for t, n in ((x, "x"), (weight, "weight"), (conv_out, "conv_out"), (rezero_weight, "rezero_weight")):
+            _require_cuda_f32(t, n)
+        B, V, Fin = x.shape
+        Fout, Fin_w = weight.shape
+        if Fin != Fin_w or tuple(conv_out.shape) != (B, V, Fout) or rezero_weight.numel() != 1:
+            raise ValueError("shape mismatch in the fused residual tail")
+        lib = _lib.load()
+        x = x.contiguous()
+        w = weight.contiguous()
+        a = conv_out.contiguous()
+        bptr = bias.contiguous().data_ptr() if bias is not None else None
+        y = torch.empty((B, V, Fout), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            ws = _workspace(lib.dsw_linear_workspace_bytes(B, V, Fin, Fout), x.device)
+            rc = lib.dsw_linear_rezero_fwd(x.data_ptr(), x.stride(0), x.stride(1), w.data_ptr(), bptr, a.data_ptr(),
+                                           rezero_weight.data_ptr(), y.data_ptr(), B, V, Fin, Fout, ws.data_ptr(), ws.numel(),
+                                           _stream_ptr(x.device))
+        _lib.check(rc, "dsw_linear_rezero_fwd")
+        ctx.save_for_backward(x, w, a, rezero_weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, w, a, rz = ctx.saved_tensors
+        lib = _lib.load()
+        B, V, Fin = x.shape
+        Fout = w.shape[0]
+        g = g.contiguous()
+        need_dx, need_dw, need_db, need_a, need_rz = ctx.needs_input_grad
+        need_db = need_db and ctx.has_bias
+        dx = torch.empty_like(x) if need_dx else None
+        dw = torch.empty_like(w) if need_dw else None
+        db = torch.empty(Fout, dtype=torch.float32, device=x.device) if need_db else None
+        da = torch.empty_like(a) if need_a else None
+        drz = torch.empty_like(rz) if need_rz else None
+        with torch.cuda.device(x.device):
+            if need_dx or need_dw or need_db:
+                ws = _workspace(lib.dsw_linear_workspace_bytes(B, V, Fin, Fout), x.device)
+                rc = lib.dsw_linear_bwd(
+                    x.data_ptr(), x.stride(0), x.stride(1), g.data_ptr(), w.data_ptr(),
+                    dx.data_ptr() if dx is not None else None, dw.data_ptr() if dw is not None else None,
+                    db.data_ptr() if db is not None else None, B, V, Fin, Fout, ws.data_ptr(), ws.numel(), _stream_ptr(x.device))
+                _lib.check(rc, "dsw_linear_bwd")
+            if need_a or need_rz:
+                ws2 = _workspace(lib.dsw_rezero_bwd_workspace_bytes(), x.device)
+                rc = lib.dsw_rezero_bwd(g.data_ptr(), a.data_ptr(), rz.data_ptr(), da.data_ptr() if da is not None else None,
+                                        drz.data_ptr() if drz is not None else None, ws2.data_ptr(), ws2.numel(), a.numel(),
+                                        _stream_ptr(x.device))
+                _lib.check(rc, "dsw_rezero_bwd")
+        return dx, dw, db, da, drz
+
+
+def linear_rezero(x, weight, bias, conv_out, rezero_weight):
+    return LinearRezeroFunction.apply(x, weight, bias, conv_out, rezero_weight)
+
+
 # --------------------------------------------------------------------------------------------
 # Sparse remap                                                     reference layers.py:956-964
 # --------------------------------------------------------------------------------------------

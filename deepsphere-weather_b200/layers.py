@@ -159,6 +159,14 @@ class NodeLinear(torch.nn.Linear):
             return y[..., : self.out_features] if pout else y
         return super().forward(x)
 
+    def forward_rezero(self, x, conv_out, rezero_weight):
+        """``self(x) + rezero_weight * conv_out`` — the ResBlock tail (``my_models_graph.py:211-215``) — in one
+        launch when the channel counts are 16-byte aligned, else the two-kernel composition."""
+        if (x.dim() == 3 and x.is_cuda and x.dtype == torch.float32 and conv_out.dtype == torch.float32
+                and _pad4(self.in_features) == 0 and _pad4(self.out_features) == 0):
+            return F_.linear_rezero(x, self.weight, self.bias, conv_out, rezero_weight)
+        return F_.rezero_residual(conv_out, self.forward(x), rezero_weight)
+
 
 # ------------------------------------------------------------------------------------------
 # Nested-order (HEALPix) pools                                    reference layers.py:784-941

@@ -13,6 +13,7 @@ classes (e.g. the oracle's); the product default is ``deepsphere_weather_b200.la
 """
 from __future__ import annotations
 
+import os
 from types import SimpleNamespace
 from typing import Dict, Optional, Sequence
 
@@ -21,6 +22,10 @@ import torch
 from torch.nn import functional as F
 
 from . import graphs as G
+
+
+# A/B switch (DSW_LINEAR_REZERO=0): two-kernel ResBlock tail instead of the fused Linear + ReZero launch
+_LINEAR_REZERO = os.environ.get("DSW_LINEAR_REZERO", "1") != "0"
 
 
 def _default_backend():
@@ -116,6 +121,8 @@ class ResBlock(torch.nn.Module):
         for name in self.conv_names_list:
             out = getattr(self, name)(out)
         if self.rezero and self._fused_tail is not None:
+            if _LINEAR_REZERO and hasattr(self.res_connection, "forward_rezero"):  # Linear skip + scale + add in one launch
+                return self.res_connection.forward_rezero(x, out, self.rezero_weight)
             return self._fused_tail(out, self.res_connection(x), self.rezero_weight)
         if self.rezero:
             out *= self.rezero_weight

@@ -201,6 +201,13 @@ int dsw_nested_sum(const float* x, int64_t x_sB, int64_t x_sV, float* y, int32_t
  * bwd: d_conv_out = w * g (nullable), d_w = sum(g * conv_out) (nullable; needs conv_out and the
  * workspace; fixed-order reduction); the gradient of `skip` is g itself.
  * ------------------------------------------------------------------------------------------- */
+/* The whole ResBlock tail in one launch when the skip is a Linear:  y = x . Wl^T + bias + scale[0] * conv_out
+ * (`x_out *= self.rezero_weight; x_out += self.res_connection(x)`, my_models_graph.py:196-201, 211-215);
+ * conv_out and y are contiguous [B, V, Fout], scale a device scalar.  Workspace as dsw_linear_fwd.  The
+ * gradients are dsw_linear_bwd (dy = g) and dsw_rezero_bwd. */
+int dsw_linear_rezero_fwd(const float* x, int64_t x_sB, int64_t x_sV, const float* Wl, const float* bias, const float* conv_out,
+                          const float* scale, float* y, int32_t B, int32_t V, int32_t Fin, int32_t Fout, void* workspace,
+                          size_t workspace_bytes, void* stream);
 int dsw_rezero_fwd(const float* conv_out, const float* skip, const float* w, float* y, int64_t n, void* stream);
 size_t dsw_rezero_bwd_workspace_bytes(void);
 int dsw_rezero_bwd(const float* g, const float* conv_out, const float* w, float* d_conv_out, float* d_w, void* workspace,

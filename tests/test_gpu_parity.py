@@ -591,6 +591,32 @@ def test_fused_relu_matches_separate_relu(Fin, Fout, fwd_algo, dev, lib, mix_mod
         layer(x, activation="tanh")
 
 
+@pytest.mark.parametrize("B,V,Fin,Fout", [(2, 768, 24, 128), (3, 500, 256, 64), (1, 130, 64, 260)])
+def test_linear_rezero_tail_matches_composition(B, V, Fin, Fout, dev, mix_mode):
+    """NodeLinear.forward_rezero (one launch: x W^T + b + w * conv_out) against the reference's sequence
+    `x_out *= rezero_weight; x_out += res_connection(x)` (my_models_graph.py:211-215) in torch on the CPU."""
+    from deepsphere_weather_b200 import layers as L
+
+    torch.manual_seed(13)
+    lin = L.NodeLinear(Fin, Fout)
+    x, a, g = torch.randn(B, V, Fin), torch.randn(B, V, Fout), torch.randn(B, V, Fout)
+    w = torch.full((1,), 0.8)
+    xr, ar, wr = x.clone().requires_grad_(True), a.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    out = ar * 1.0
+    out *= wr
+    out += torch.nn.functional.linear(xr, lin.weight, lin.bias)
+    out.backward(g)
+    ref = [xr.grad, lin.weight.grad.clone(), lin.bias.grad.clone(), ar.grad, wr.grad]
+    lin.zero_grad(set_to_none=True)
+    lin = lin.to(dev)
+    xd, ad, wd = (t.to(dev).requires_grad_(True) for t in (x, a, w))
+    y = lin.forward_rezero(xd, ad, wd)
+    y.backward(g.to(dev))
+    assert rel_err(y, out.detach()) < REL_TOL
+    for got, want in zip([xd.grad, lin.weight.grad, lin.bias.grad, ad.grad, wd.grad], ref):
+        assert rel_err(got, want) < REL_TOL
+
+
 def test_hops_replay_in_a_cuda_graph(dev):
     """The dynamically scheduled hop kernel keeps claim counters in the plan; they must be back to
     zero after every launch so that replays of a captured CUDA graph (same counter set every time)
