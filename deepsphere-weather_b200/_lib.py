@@ -11,7 +11,7 @@ import os
 import re
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libdsw.so")
+LIB_PATH = os.environ.get("DSW_LIB_PATH") or os.path.join(PKG_DIR, "libdsw.so")  # (override: A/B of two builds)
 HEADER_PATH = os.path.join(os.path.dirname(PKG_DIR), "include", "dsw.h")
 
 _i32, _i64, _f32 = C.c_int32, C.c_int64, C.c_float
@@ -94,6 +94,8 @@ def load():
         )
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
+        if "DSW_LIB_PATH" in os.environ and not hasattr(lib, name):
+            continue  # an older build under A/B test; calling the missing entry point raises AttributeError
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

@@ -472,6 +472,9 @@ constexpr int EPI_PITCH = 64;                          // floats per staged row;
 constexpr int EPI_BYTES = 32 * EPI_PITCH * 4;          // one warp's 32 x 64 staging chunk
 __device__ __forceinline__ int epi_off(int row, int chunk) { return row * EPI_PITCH + ((chunk ^ (row & 15)) << 2); }
 
+// ADDEND: the epilogue also adds r_scale * R (MixArgs); a separate instantiation so that the plain kernel's
+// register allocation is untouched.
+template <bool ADDEND>
 __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_constant__ TmaArgs Q) {
   extern __shared__ uint8_t smem_raw[];
   pdl_trigger();
@@ -674,7 +677,7 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
           const bool vec = vec_ok && (col + 3 < a.Nc) && (ccol + 3 < a.Cw);
           float* cbase = a.C + (int64_t)cp * a.sCp + ccol;
           const bool relu = a.act == 1;
-          if (vec && a.R != nullptr) {
+          if (ADDEND && vec && a.R != nullptr) {
             // same, plus the addend row segments (C += r_scale * R): their global loads are issued first
             const float rs = a.r_scale ? __ldg(a.r_scale) : 1.f;
             const bool r_vec = (a.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.R) & 15) == 0);
@@ -735,7 +738,7 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 if (col + e >= a.Nc) break;
-                if (a.R) ve[e] = fmaf(a.r_scale ? __ldg(a.r_scale) : 1.f, __ldg(a.R + n * a.ldr + col + e), ve[e]);
+                if (ADDEND && a.R) ve[e] = fmaf(a.r_scale ? __ldg(a.r_scale) : 1.f, __ldg(a.R + n * a.ldr + col + e), ve[e]);
                 const int cpe = (col + e) / a.Cw, cce = (col + e) - cpe * a.Cw;
                 a.C[(int64_t)cpe * a.sCp + n * a.ldc + cce] = relu ? fmaxf(ve[e], 0.f) : ve[e];
               }
@@ -859,10 +862,16 @@ int launch_mix_tc_ws(const MixArgs& a, void* prep, size_t prep_bytes, bool do_pr
     Q.tc.stages = tc::tma_stages_for(P.BN);
     if (tc::encode_a_maps(a, &Q)) {
       const size_t smem = tc::tma_smem_bytes_for(P.BN);
-      static std::atomic<bool> attr_tma{false};
-      if (!attr_tma.exchange(true))
-        DSW_CUDA_TRY(cudaFuncSetAttribute(tc::mix_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      DSW_CUDA_TRY(launch_pdl(tc::mix_tma_kernel, grid, dim3(tc::THREADS2), smem, st, pdl_enabled(), Q));
+      static std::atomic<bool> attr_tma[2] = {{false}, {false}};
+      if (a.R != nullptr) {
+        if (!attr_tma[1].exchange(true))
+          DSW_CUDA_TRY(cudaFuncSetAttribute(tc::mix_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DSW_CUDA_TRY(launch_pdl(tc::mix_tma_kernel<true>, grid, dim3(tc::THREADS2), smem, st, pdl_enabled(), Q));
+      } else {
+        if (!attr_tma[0].exchange(true))
+          DSW_CUDA_TRY(cudaFuncSetAttribute(tc::mix_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DSW_CUDA_TRY(launch_pdl(tc::mix_tma_kernel<false>, grid, dim3(tc::THREADS2), smem, st, pdl_enabled(), Q));
+      }
       return check_launch();
     }
   }
