@@ -53,6 +53,34 @@ def test_bad_arguments_are_rejected_without_a_gpu(lib):
     assert not handle.value
 
 
+def test_new_entry_points_validate_arguments_without_a_gpu(lib):
+    assert lib.dsw_rezero_bwd_workspace_bytes() >= 4
+    assert lib.dsw_rezero_fwd(None, None, None, None, 16, None) < 0
+    assert lib.dsw_rezero_bwd(None, None, None, None, None, None, 0, 16, None) < 0
+    assert lib.dsw_linear_rezero_fwd(None, 0, 0, None, None, None, None, None, 1, 1, 4, 4, None, 0, None) < 0
+    assert lib.dsw_debug_dense_counters(None, 0) < 0
+
+
+def test_tuning_options_round_trip_and_env_hook(lib):
+    """dsw_set_option / dsw_get_option and the DSW_OPTIONS="key=value,..." hook of _lib.load()."""
+    import re
+    import subprocess
+
+    with open(_lib.HEADER_PATH) as f:
+        count = int(re.search(r"DSW_OPT_COUNT\s*=\s*(\d+)", f.read()).group(1))
+    for key in range(count):
+        prev = lib.dsw_get_option(key)
+        assert lib.dsw_set_option(key, 3) == 0 and lib.dsw_get_option(key) == 3
+        assert lib.dsw_set_option(key, prev) == 0
+    assert lib.dsw_set_option(count, 1) < 0 and lib.dsw_set_option(0, -1) < 0 and lib.dsw_get_option(count) == -1
+    code = ("import sys; sys.path.insert(0, %r); from deepsphere_weather_b200 import _lib; l = _lib.load(); "
+            "print(l.dsw_get_option(15), l.dsw_get_option(14))" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, DSW_OPTIONS="15=1,14=2"), capture_output=True, text=True)
+    assert out.stdout.split() == ["1", "2"], out.stderr[-400:]
+    bad = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, DSW_OPTIONS="999=1"), capture_output=True, text=True)
+    assert bad.returncode != 0
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
 def test_no_cpu_fallback():
     from deepsphere_weather_b200 import functional as F_
