@@ -56,6 +56,7 @@ struct dsw_rb {
   // set) and the host-side launch counter that picks the set.
   int32_t* hop_cnt = nullptr;               // [HOP_CNT_SLOTS][n_tiles + 1]
   std::atomic<uint32_t>* hop_ring = nullptr;
+  int32_t* perm = nullptr;     // locality permutation: original row of permuted position p ([n_blocks * R], -1 = padding) or null
   int32_t* blkptr = nullptr;   // [n_blocks + 1] offsets into ucol / uval panels
   int32_t* ucol = nullptr;     // [total_union]
   float* uval = nullptr;       // [total_union * R]  (entry u, row r) at uval[u*R + r]

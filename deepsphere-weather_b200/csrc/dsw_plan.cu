@@ -71,6 +71,7 @@ static HostCsr transpose(const HostCsr& a) {
 
 struct HostRb {
   int32_t R = 0, n_blocks = 0, max_union = 0;
+  std::vector<int32_t> perm;  // original row of permuted position p (padded to n_blocks * R with -1); empty = natural order
   std::vector<int32_t> blkptr, ucol;
   std::vector<float> uval;
   // tiles of DSW_TILE_BLOCKS row-blocks
@@ -151,30 +152,134 @@ static void build_tiles(HostRb& rb) {
   }
 }
 
-static HostRb build_rb(const HostCsr& a, int32_t R) {
+// `order` (optional): permuted position -> original row; row-block b then holds rows order[b*R .. b*R+R-1].
+static HostRb build_rb(const HostCsr& a, int32_t R, const std::vector<int32_t>* order = nullptr) {
   HostRb rb;
   rb.R = R;
   rb.n_blocks = (a.n_rows + R - 1) / R;
+  if (order) {
+    rb.perm = *order;
+    rb.perm.resize(static_cast<size_t>(rb.n_blocks) * R, -1);
+  }
   rb.blkptr.assign(static_cast<size_t>(rb.n_blocks) + 1, 0);
   std::vector<int32_t> uni;
+  int32_t rows[8];
   for (int32_t blk = 0; blk < rb.n_blocks; ++blk) {
-    const int32_t r0 = blk * R, r1 = std::min(a.n_rows, r0 + R);
-    uni.assign(a.col.begin() + a.rowptr[r0], a.col.begin() + a.rowptr[r1]);
+    for (int32_t r = 0; r < R; ++r) {
+      const int32_t pos = blk * R + r;
+      rows[r] = order ? rb.perm[pos] : (pos < a.n_rows ? pos : -1);
+    }
+    uni.clear();
+    for (int32_t r = 0; r < R; ++r)
+      if (rows[r] >= 0) uni.insert(uni.end(), a.col.begin() + a.rowptr[rows[r]], a.col.begin() + a.rowptr[rows[r] + 1]);
     std::sort(uni.begin(), uni.end());
     uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
     const size_t base = rb.ucol.size();
     rb.ucol.insert(rb.ucol.end(), uni.begin(), uni.end());
     rb.uval.resize((base + uni.size()) * R, 0.f);
-    for (int32_t row = r0; row < r1; ++row)
-      for (int32_t e = a.rowptr[row]; e < a.rowptr[row + 1]; ++e) {
+    for (int32_t r = 0; r < R; ++r) {
+      if (rows[r] < 0) continue;
+      for (int32_t e = a.rowptr[rows[r]]; e < a.rowptr[rows[r] + 1]; ++e) {
         const size_t u = std::lower_bound(uni.begin(), uni.end(), a.col[e]) - uni.begin();
-        rb.uval[(base + u) * R + (row - r0)] = a.val[e];
+        rb.uval[(base + u) * R + r] = a.val[e];
       }
+    }
     rb.blkptr[blk + 1] = static_cast<int32_t>(rb.ucol.size());
     rb.max_union = std::max<int32_t>(rb.max_union, static_cast<int32_t>(uni.size()));
   }
   if (R == 4) build_tiles(rb);
   return rb;
+}
+
+// Locality-preserving row order for operators whose natural order has none (e.g. a row-major lat-lon grid:
+// 64 consecutive nodes are a strip, and a tile of the hop kernel would gather ~2.5x more source rows than
+// a compact patch).  Greedy region growing over the operator's own graph: clusters of one tile's worth of rows
+// are grown breadth-first from a seed; the next seed is the oldest still-unvisited row on the frontier of what
+// has been clustered so far, so that consecutive clusters are adjacent too.  Square operators only.
+static std::vector<int32_t> locality_order(const HostCsr& a, int32_t cluster_rows) {
+  const int32_t n = a.n_rows;
+  std::vector<int32_t> order;
+  order.reserve(n);
+  std::vector<uint8_t> state(n, 0);  // 0 = untouched, 1 = on the global frontier, 2 = clustered
+  std::vector<int32_t> frontier, queue;
+  std::vector<int32_t> stamp(a.n_cols, 0);
+  int32_t stamp_id = 0;
+  size_t frontier_head = 0;
+  int32_t next_natural = 0;
+  while (static_cast<int32_t>(order.size()) < n) {
+    int32_t seed = -1;
+    while (frontier_head < frontier.size()) {
+      const int32_t c = frontier[frontier_head++];
+      if (state[c] != 2) { seed = c; break; }
+    }
+    if (seed < 0) {
+      while (state[next_natural] == 2) ++next_natural;
+      seed = next_natural;
+    }
+    queue.clear();
+    queue.push_back(seed);
+    state[seed] = 2;
+    for (size_t head = 0; head < queue.size(); ++head) {
+      const int32_t r = queue[head];
+      for (int32_t e = a.rowptr[r]; e < a.rowptr[r + 1]; ++e) {
+        const int32_t c = a.col[e];
+        if (c < n && state[c] != 2 && static_cast<int32_t>(queue.size()) < cluster_rows) {
+          state[c] = 2;
+          queue.push_back(c);
+        } else if (c < n && state[c] == 0) {
+          state[c] = 1;
+          frontier.push_back(c);
+        }
+      }
+    }
+    // Inside the cluster, group the rows four by four (one row-block) so that a group's rows share as many
+    // columns as possible: start from the oldest ungrouped row, then add three times the ungrouped row with
+    // the largest overlap with the group's column union.
+    std::vector<uint8_t> used(queue.size(), 0);
+    for (size_t first = 0; first < queue.size(); ++first) {
+      if (used[first]) continue;
+      used[first] = 1;
+      order.push_back(queue[first]);
+      ++stamp_id;
+      for (int32_t e = a.rowptr[queue[first]]; e < a.rowptr[queue[first] + 1]; ++e) stamp[a.col[e]] = stamp_id;
+      for (int pick = 0; pick < 3; ++pick) {
+        int best = -1, best_overlap = -1;
+        for (size_t i = first + 1; i < queue.size(); ++i) {
+          if (used[i]) continue;
+          int overlap = 0;
+          for (int32_t e = a.rowptr[queue[i]]; e < a.rowptr[queue[i] + 1]; ++e) overlap += stamp[a.col[e]] == stamp_id;
+          if (overlap > best_overlap) best_overlap = overlap, best = static_cast<int>(i);
+        }
+        if (best < 0) break;
+        used[best] = 1;
+        order.push_back(queue[best]);
+        for (int32_t e = a.rowptr[queue[best]]; e < a.rowptr[queue[best] + 1]; ++e) stamp[a.col[e]] = stamp_id;
+      }
+    }
+  }
+  return order;
+}
+
+static double avg_tile_rows(const HostRb& rb) {
+  return rb.n_tiles > 0 ? static_cast<double>(rb.tile_row.size()) / rb.n_tiles : 0.0;
+}
+
+// Row-block layout in the natural order, or — when that order gathers far more source rows per tile than a
+// compact patch would and the region-grown order is clearly better — in the locality order.
+static HostRb build_rb_auto(const HostCsr& a, int32_t R) {
+  HostRb nat = build_rb(a, R);
+  const int64_t opt = g_options[DSW_OPT_PLAN_PERMUTE].load(std::memory_order_relaxed);  // 0 auto, 1 never, 2 always
+  if (R != 4 || a.n_rows != a.n_cols || nat.n_tiles < 4 || opt == 1) return nat;
+  const double rows_per_tile = 4.0 * DSW_TILE_BLOCKS;
+  // Automatic mode permutes only when the natural order is hopeless (a tile would gather > 6x its own rows, e.g.
+  // randomly numbered nodes: the tile kernel would not even fit two teams).  A row-major lat-lon grid (4.4x,
+  // cfg5) measured 8 % *slower* permuted: the region-grown patches need 3-4x more, smaller TMA boxes.
+  if (opt != 2 && avg_tile_rows(nat) < 6.0 * rows_per_tile) return nat;
+  const std::vector<int32_t> order = locality_order(a, 4 * DSW_TILE_BLOCKS);
+  HostRb loc = build_rb(a, R, &order);
+  if (loc.n_tiles == 0) return nat;
+  if (opt != 2 && avg_tile_rows(loc) > 0.85 * avg_tile_rows(nat)) return nat;
+  return loc;
 }
 
 // Cost model (cycles per row-block per 64 features, one SM): gathers cost 2 cycles of the 128 B/clk
@@ -236,6 +341,7 @@ static cudaError_t upload_rb(dsw_rb* d, const HostRb& h, cudaStream_t st) {
   if ((e = upload(&d->blkptr, h.blkptr, st)) != cudaSuccess) return e;
   if ((e = upload(&d->ucol, h.ucol, st)) != cudaSuccess) return e;
   if ((e = upload(&d->uval, h.uval, st)) != cudaSuccess) return e;
+  if (!h.perm.empty() && (e = upload(&d->perm, h.perm, st)) != cudaSuccess) return e;
   d->n_tiles = h.n_tiles;
   d->tile_rows_max = h.tile_rows_max;
   if (h.n_tiles > 0) {
@@ -279,6 +385,7 @@ static void free_rb(dsw_rb* r) {
   cudaFree(r->tp_ptr);
   cudaFree(r->tp_val);
   cudaFree(r->tp_off);
+  cudaFree(r->perm);
   cudaFree(r->hop_cnt);
   delete r->hop_ring;
   *r = dsw_rb{};
@@ -365,11 +472,11 @@ int dsw_plan_create(int32_t n_rows, int32_t n_cols, int64_t nnz, const int64_t* 
   if (e == cudaSuccess) e = upload_csr(&p->tr, tr, st);
   if (e == cudaSuccess) {
     const int32_t rf = pick_rb_rows(fwd);
-    if (rf > 0) e = upload_rb(&p->fwd_rb, build_rb(fwd, rf), st);
+    if (rf > 0) e = upload_rb(&p->fwd_rb, build_rb_auto(fwd, rf), st);
   }
   if (e == cudaSuccess) {
     const int32_t rt = pick_rb_rows(tr);
-    if (rt > 0) e = upload_rb(&p->tr_rb, build_rb(tr, rt), st);
+    if (rt > 0) e = upload_rb(&p->tr_rb, build_rb_auto(tr, rt), st);
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // host vectors go out of scope
   if (e != cudaSuccess) {

@@ -330,6 +330,7 @@ struct TeamHopPlan {
   int32_t n_ctas;         // CTAs of this launch (the last one to leave zeroes the counters again)
   int32_t prefetch_zg;    // 1 = L2-prefetch the next item's Z / G rows when its tile transfer is issued
   int32_t pdl;            // 1 = launched with programmatic stream serialisation: the prologue may overlap the previous kernel
+  const int32_t* perm;    // PERM kernels: original row id of every permuted row position ([n_blocks * 4], -1 = padding)
   int32_t debug_skip;     // timing experiments only: 1 = skip staging, 2 = skip the entry loop
 };
 
@@ -397,7 +398,9 @@ __device__ __noinline__ void hop_prefetch_zg(const float* z, int64_t z_sV, const
 
 // LPR = lanes per row-block: 4 (a lane holds 4 rows x 16 channels) or 8 (4 rows x 8 channels: twice the
 // warps per team and half the registers per lane).
-template <bool TMA, int LPR>
+// PERM: the plan tiles a locality-preserving permutation of the rows (orderings without locality, e.g.
+// row-major lat-lon grids): row-block position p holds original row P.perm[p].
+template <bool TMA, int LPR, bool PERM>
 __global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
     hop_team_kernel(const TeamHopPlan P, const HopArgs a, const __grid_constant__ HopMaps maps) {
   extern __shared__ __align__(256) uint8_t tile_smem[];
@@ -495,7 +498,7 @@ __global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
       }
       // pull the item's Z / G rows (read at the top of the item, straight into the accumulators) towards
       // L2 now, while the current item's stores and the tile transfer are in flight
-      if (P.prefetch_zg && (a.Z != nullptr || a.G != nullptr)) {
+      if (!PERM && P.prefetch_zg && (a.Z != nullptr || a.G != nullptr)) {
         const int64_t row0 = (int64_t)blk0 * 4;
         const int rows = (int)min((int64_t)(4 * DSW_TILE_BLOCKS), (int64_t)P.n_rows - row0);
         hop_prefetch_zg(a.Z ? a.Z + b * a.z_sB + row0 * a.z_sV + slab * 64 : nullptr, a.z_sV,
@@ -546,6 +549,13 @@ __global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
   const int slot = tt / LPR, lq = tt % LPR, par = slot & 1;
   const int blk = blk0 + slot;
   const bool active = blk < P.n_blocks;
+  // original row of each of the row-block's 4 rows (-1 = none)
+  int orow[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int pos = blk * 4 + r;
+    orow[r] = !active ? -1 : PERM ? __ldg(P.perm + pos) : (pos < P.n_rows ? pos : -1);
+  }
   int my_len = 0;
   if (active) my_len = __ldg(P.blkptr + blk + 1) - __ldg(P.blkptr + blk);
   // uniform trip count of the warp (8 row-blocks), rounded up to the 2-step pipeline
@@ -590,7 +600,7 @@ __global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-          ok[r][j] = active && (blk * 4 + r) < P.n_rows && ch[j] < slab_f;
+          ok[r][j] = orow[r] >= 0 && ch[j] < slab_f;
           eoff[r][j] = (int64_t)slab * 64 + ch[j];
         }
       // batch 1: all Z loads in flight together
@@ -599,7 +609,7 @@ __global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
           acc[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (a.Z != nullptr && ok[r][j]) acc[r][j] = ldcg4(a.Z + b * a.z_sB + (int64_t)(blk * 4 + r) * a.z_sV + eoff[r][j]);
+          if (a.Z != nullptr && ok[r][j]) acc[r][j] = ldcg4(a.Z + b * a.z_sB + (int64_t)orow[r] * a.z_sV + eoff[r][j]);
         }
 #pragma unroll
       for (int r = 0; r < 4; ++r)
@@ -614,7 +624,7 @@ __global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
 #pragma unroll
           for (int j = 0; j < NJ; ++j) {
             g[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok[r][j]) g[r][j] = ldcg4(a.G + b * a.g_sB + (int64_t)(blk * 4 + r) * a.g_sV + eoff[r][j]);
+            if (ok[r][j]) g[r][j] = ldcg4(a.G + b * a.g_sB + (int64_t)orow[r] * a.g_sV + eoff[r][j]);
           }
 #pragma unroll
         for (int r = 0; r < 4; ++r)
@@ -674,8 +684,8 @@ __global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
     if (active) {
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
-        const int row = blk * 4 + r;
-        if (row >= P.n_rows) break;
+        const int row = orow[r];
+        if (row < 0) continue;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
           if (ch[j] >= slab_f) continue;
@@ -791,7 +801,7 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
       const bool lpr8 = g_options[DSW_OPT_HOP_LPR].load(std::memory_order_relaxed) == 8;
       P.pdl = g_options[DSW_OPT_NO_PDL].load(std::memory_order_relaxed) == 0 ? 1 : 0;
       auto launch = [&](auto kern, int threads, int slot) -> int {
-        static std::atomic<bool> attr_done[4] = {{false}, {false}, {false}, {false}};
+        static std::atomic<bool> attr_done[6] = {{false}, {false}, {false}, {false}, {false}, {false}};
         if (!attr_done[slot].exchange(true))
           DSW_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         if (P.pdl) {
@@ -807,13 +817,18 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
         }
         return check_launch();
       };
-      if (tma) return lpr8 ? launch(hop_team_kernel<true, 8>, DSW_TILE_BLOCKS * 8 * MAX_TEAMS, 0)
-                           : launch(hop_team_kernel<true, 4>, DSW_TILE_BLOCKS * 4 * MAX_TEAMS, 1);
-      return lpr8 ? launch(hop_team_kernel<false, 8>, DSW_TILE_BLOCKS * 8 * MAX_TEAMS, 2)
-                  : launch(hop_team_kernel<false, 4>, DSW_TILE_BLOCKS * 4 * MAX_TEAMS, 3);
+      P.perm = rb.perm;
+      if (rb.perm) {  // permuted plans: 4 lanes per row-block only
+        if (tma) return launch(hop_team_kernel<true, 4, true>, DSW_TILE_BLOCKS * 4 * MAX_TEAMS, 4);
+        return launch(hop_team_kernel<false, 4, true>, DSW_TILE_BLOCKS * 4 * MAX_TEAMS, 5);
+      }
+      if (tma) return lpr8 ? launch(hop_team_kernel<true, 8, false>, DSW_TILE_BLOCKS * 8 * MAX_TEAMS, 0)
+                           : launch(hop_team_kernel<true, 4, false>, DSW_TILE_BLOCKS * 4 * MAX_TEAMS, 1);
+      return lpr8 ? launch(hop_team_kernel<false, 8, false>, DSW_TILE_BLOCKS * 8 * MAX_TEAMS, 2)
+                  : launch(hop_team_kernel<false, 4, false>, DSW_TILE_BLOCKS * 4 * MAX_TEAMS, 3);
     }
   }
-  if (v4 && rb.R == 4 && hop_mode == 3 && off32 && rb.tile_entries_max > 0) {
+  if (v4 && rb.R == 4 && hop_mode == 3 && off32 && rb.tile_entries_max > 0 && !rb.perm) {
     const size_t smem = (size_t)((rb.tile_entries_max + 3) & ~3) * 20;
     const int n_tiles = ceil_div(rb.n_blocks, TILE_BLOCKS);
     if (smem <= 200 * 1024) {
@@ -838,7 +853,7 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
       return check_launch();
     }
   }
-  if (v4 && rb.R > 0 && hop_mode <= 1 && a.F > small_f) {
+  if (v4 && rb.R > 0 && hop_mode <= 1 && a.F > small_f && !rb.perm) {
     const int threads = 512;
     const int slots = threads / 16;
     dim3 grid(ceil_div(rb.n_blocks, slots), ceil_div(a.F, 64), a.B);

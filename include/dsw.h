@@ -241,7 +241,8 @@ enum {
   DSW_OPT_HOP_TEAMS = 13,     /* cap on the teams per hop CTA (0 = as many as shared memory holds, up to 5) */
   DSW_OPT_HOP_PREFETCH = 14,  /* the hop kernel L2-prefetches the next item's Z / G rows when it issues its tile transfer (default); 2 = off */
   DSW_OPT_NO_PDL = 15,        /* 1 = launch the hop kernel without programmatic stream serialisation */
-  DSW_OPT_COUNT = 16
+  DSW_OPT_PLAN_PERMUTE = 16,  /* locality permutation of the row-block layout at plan creation: 0 = automatic, 1 = never, 2 = always */
+  DSW_OPT_COUNT = 17
 };
 /* Tuning only: with DSW_OPT_DEBUG = 4 the hop kernel sums per-phase SM cycles over its teams
  * (issue staging, wait for tile + Z/G, entry loop, stores, item count). */

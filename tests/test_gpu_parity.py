@@ -617,6 +617,51 @@ def test_linear_rezero_tail_matches_composition(B, V, Fin, Fout, dev, mix_mode):
         assert rel_err(got, want) < REL_TOL
 
 
+@pytest.mark.parametrize("mode", ["forced-on-nested", "auto-on-shuffled"])
+def test_locality_permuted_plan_matches_oracle(mode, dev, lib):
+    """Plans may tile a locality-preserving permutation of the rows (DSW_OPT_PLAN_PERMUTE; automatic for
+    orderings without locality).  Forward, input gradient and weight gradient must not change."""
+    from deepsphere_weather_b200 import functional as F_
+    from deepsphere_weather_b200 import graphs as G
+    from deepsphere_weather_b200 import layers as L
+    from oracle import cheb_oracle as O
+
+    torch.manual_seed(21)
+    lap = G.healpix_laplacian(8)
+    V = lap.shape[0]
+    if mode == "auto-on-shuffled":  # the same graph with its nodes renumbered at random: no locality left
+        p = torch.randperm(V)
+        c = lap.coalesce()
+        inv = torch.empty(V, dtype=torch.int64)
+        inv[p] = torch.arange(V)
+        lap = torch.sparse_coo_tensor(inv[c.indices()], c.values(), c.shape).coalesce()
+    B, Fin, Fout, K = 3, 72, 40, 4
+    x, dy = torch.randn(B, V, Fin), torch.randn(B, V, Fout)
+    w, b = torch.randn(Fin, K, Fout) * 0.05, torch.randn(Fout) * 0.1
+    xo, wo, bo = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yo = O.conv_cheb_layer(lap, xo, wo, bo)
+    yo.backward(dy)
+    F_._PLAN_CACHE.clear()
+    lib.dsw_set_option(16, 2 if mode == "forced-on-nested" else 0)
+    try:
+        for fwd_algo, bwd_algo in [(1, 2), (2, 1)]:
+            lib.dsw_set_option(4, fwd_algo)
+            lib.dsw_set_option(5, bwd_algo)
+            layer = L.ConvCheb(Fin, Fout, K, lap).to(dev)
+            layer.set_parameters(w.to(dev), b.to(dev))
+            xg = x.to(dev).requires_grad_(True)
+            yg = layer(xg)
+            yg.backward(dy.to(dev))
+            assert rel_err(yg, yo) < REL_TOL
+            assert rel_err(xg.grad, xo.grad) < REL_TOL
+            assert rel_err(layer.weight.grad, wo.grad) < REL_TOL
+            assert rel_err(layer.bias.grad, bo.grad) < REL_TOL
+    finally:
+        for key in (4, 5, 16):
+            lib.dsw_set_option(key, 0)
+        F_._PLAN_CACHE.clear()
+
+
 def test_hops_replay_in_a_cuda_graph(dev):
     """The dynamically scheduled hop kernel keeps claim counters in the plan; they must be back to
     zero after every launch so that replays of a captured CUDA graph (same counter set every time)
