@@ -644,9 +644,10 @@ def test_locality_permuted_plan_matches_oracle(mode, dev, lib):
     F_._PLAN_CACHE.clear()
     lib.dsw_set_option(16, 2 if mode == "forced-on-nested" else 0)
     try:
-        for fwd_algo, bwd_algo in [(1, 2), (2, 1)]:
+        for fwd_algo, bwd_algo, no_tma in [(1, 2, 0), (2, 1, 0), (1, 1, 1)]:
             lib.dsw_set_option(4, fwd_algo)
             lib.dsw_set_option(5, bwd_algo)
+            lib.dsw_set_option(3, no_tma)  # the cp.async staging variant of the permuted kernel as well
             layer = L.ConvCheb(Fin, Fout, K, lap).to(dev)
             layer.set_parameters(w.to(dev), b.to(dev))
             xg = x.to(dev).requires_grad_(True)
@@ -657,7 +658,7 @@ def test_locality_permuted_plan_matches_oracle(mode, dev, lib):
             assert rel_err(layer.weight.grad, wo.grad) < REL_TOL
             assert rel_err(layer.bias.grad, bo.grad) < REL_TOL
     finally:
-        for key in (4, 5, 16):
+        for key in (3, 4, 5, 16):
             lib.dsw_set_option(key, 0)
         F_._PLAN_CACHE.clear()
 
