@@ -586,30 +586,31 @@ __global__ void __launch_bounds__(T_THREADS, 1) wgrad_tma_kernel(const __grid_co
       }
     }
 
-    // ---- dbias partial (fp32, CTA-local reduction through shared memory) ----
-    if (do_bias) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (j < nbl && (ub0 + j) * 64 < Fu) {
-          atomicAdd(&bias_acc[(ub0 + j) * 64 + q * 4 + 0], bsum[j].x);
-          atomicAdd(&bias_acc[(ub0 + j) * 64 + q * 4 + 1], bsum[j].y);
-          atomicAdd(&bias_acc[(ub0 + j) * 64 + q * 4 + 2], bsum[j].z);
-          atomicAdd(&bias_acc[(ub0 + j) * 64 + q * 4 + 3], bsum[j].w);
-        }
-      }
-    }
     asm volatile("bar.sync 1, %0;" ::"n"(T_CONV) : "memory");
 
     // ================= epilogue: TMEM -> partial[split] =================
     const int64_t prow = (int64_t)a.K * a.Fin + 1;
     float* __restrict__ Pp = a.partial + (int64_t)split * prow * a.Fout;
-    if (do_bias && t < BN && (t >> 6) >= ub0 && (t >> 6) < ub0 + nbl && o_base + t < a.Fout)
-      Pp[(prow - 1) * a.Fout + o_base + t] = bias_acc[t];
 
     if (nkb > 0) {
       const int last = nkb - 1;
       mbar_wait(empty(last % S), (uint32_t)(last / S) & 1);
       tc_fence_after();
+    }
+    // ---- dbias partial: fixed-order reduction of the 16 row groups through the (now idle) first stage ----
+    if (do_bias) {
+      float4* red = reinterpret_cast<float4*>(smem_gen);  // [r0 (16)][unit (4)][q (16)] float4 = 16 KB
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[(r0 * 4 + j) * 16 + q] = bsum[j];
+      asm volatile("bar.sync 1, %0;" ::"n"(T_CONV) : "memory");
+      const int unit = t >> 6, within = t & 63;  // column t of the N tile = unit, float4 q = within / 4, lane within % 4
+      if (t < BN && unit >= ub0 && unit < ub0 + nbl && unit * 64 < Fu && o_base + t < a.Fout) {
+        const float* redf = reinterpret_cast<const float*>(red);
+        float sum = 0.f;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) sum += redf[(((g * 4 + (unit - ub0)) * 16) + (within >> 2)) * 4 + (within & 3)];
+        Pp[(prow - 1) * a.Fout + o_base + t] = sum;
+      }
     }
     const int quarter = warp & 3, part = warp >> 2;  // 4 lane quarters x 2 column parts
     const int L = quarter * 32 + lane;
