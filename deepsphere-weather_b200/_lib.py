@@ -46,6 +46,11 @@ SIGNATURES = {
     "dsw_rezero_fwd": (C.c_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
     "dsw_rezero_bwd_workspace_bytes": (_sz, []),
     "dsw_rezero_bwd": (C.c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _i64, _ptr]),
+    "dsw_wmse_workspace_bytes": (_sz, []),
+    "dsw_wmse_fwd": (C.c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _sz, _i32, _i32, _i32, _i32, _ptr]),
+    "dsw_wmse_bwd": (C.c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _ptr]),
+    "dsw_wmse_none_fwd": (C.c_int, [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _ptr]),
+    "dsw_wmse_none_bwd": (C.c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _ptr]),
     "dsw_spmm_fwd": (C.c_int, [_ptr, _ptr, _i64, _i64, _ptr, _i32, _i32, _ptr]),
     "dsw_spmm_bwd": (C.c_int, [_ptr, _ptr, _i64, _i64, _ptr, _i32, _i32, _ptr]),
     "dsw_maxval_pool_fwd": (C.c_int, [_ptr, _ptr, _i64, _i64, _ptr, _ptr, _ptr, _i32, _i32, _ptr]),

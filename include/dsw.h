@@ -214,6 +214,24 @@ int dsw_rezero_bwd(const float* g, const float* conv_out, const float* w, float*
                    size_t workspace_bytes, int64_t n, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Area-weighted MSE loss of the training loop (reference modules/loss.py:118-148 WeightedMSELoss.forward):
+ * weighted = weights[v] * (pred - label)^2 on contiguous [B, V, F]; weights [V] or null (= ones).
+ * reduction 0 = "mean" (sum / sum(weights) / B / F), 1 = "sum" (the plain sum: the reference's `* len(weights)` acts on
+ * the [1, V, 1] view, loss.py:141-144); "none" has its own pair.
+ * dsw_wmse_fwd writes the scalar loss and keeps d loss / d sum in the workspace for dsw_wmse_bwd
+ * (grad_pred = grad_out[0] * 2 * scale * weights[v] * (pred - label)); fixed-order reductions.
+ * ------------------------------------------------------------------------------------------- */
+size_t dsw_wmse_workspace_bytes(void);
+int dsw_wmse_fwd(const float* pred, const float* label, const float* weights, float* loss, void* workspace, size_t workspace_bytes,
+                 int32_t B, int32_t V, int32_t F, int32_t reduction, void* stream);
+int dsw_wmse_bwd(const float* pred, const float* label, const float* weights, const void* workspace, const float* grad_out,
+                 float* grad_pred, int32_t B, int32_t V, int32_t F, void* stream);
+int dsw_wmse_none_fwd(const float* pred, const float* label, const float* weights, float* out, int32_t B, int32_t V, int32_t F,
+                      void* stream);
+int dsw_wmse_none_bwd(const float* pred, const float* label, const float* weights, const float* grad_out, float* grad_pred, int32_t B,
+                      int32_t V, int32_t F, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Introspection used by bench.py / tests.
  * ------------------------------------------------------------------------------------------- */
 /* Number of kernels launched by this library since process start (all threads). */

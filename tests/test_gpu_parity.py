@@ -683,6 +683,38 @@ def test_gradients_are_bitwise_reproducible(dev, lib):
         assert torch.equal(p, q)
 
 
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_weighted_mse_matches_reference_golden(tag, dev):
+    """WeightedMSELoss (modules/loss.py:118-148) on the CUDA library against vectors made by the unmodified
+    reference class: all reductions, with and without node weights, values and gradients."""
+    from deepsphere_weather_b200.losses import WeightedMSELoss
+
+    g = golden("wmse")
+    w = torch.from_numpy(g[f"{tag}_w"])
+    label = torch.from_numpy(g[f"{tag}_label"]).to(dev)
+    for red in ("mean", "sum", "none"):
+        for use_w in (True, False):
+            key = f"{tag}_{red}_{'w' if use_w else 'u'}"
+            crit = WeightedMSELoss(reduction=red, weights=w.clone() if use_w else None)
+            pred = torch.from_numpy(g[f"{tag}_pred"]).to(dev).requires_grad_(True)
+            val = crit(pred, label)
+            assert rel_err(val, g[key]) < 1e-5, key
+            if red != "none":
+                val.backward()
+                assert rel_err(pred.grad, g[key + "_grad"]) < 1e-5, key
+            else:
+                up = torch.randn_like(val)
+                val.backward(up)
+                ref = 2 * up.cpu() * (w.view(1, -1, 1) if use_w else 1.0) * (torch.from_numpy(g[f"{tag}_pred"]) - label.cpu())
+                assert rel_err(pred.grad, ref) < 1e-5, key
+    with pytest.raises(ValueError):
+        WeightedMSELoss(weights=torch.ones(3))(torch.zeros(1, 4, 1, device=dev), torch.zeros(1, 4, 1, device=dev))
+    with pytest.raises(TypeError):
+        WeightedMSELoss(weights=[1.0, 2.0])
+    with pytest.raises(ValueError):
+        WeightedMSELoss(reduction="median")
+
+
 def test_hops_replay_in_a_cuda_graph(dev):
     """The dynamically scheduled hop kernel keeps claim counters in the plan; they must be back to
     zero after every launch so that replays of a captured CUDA graph (same counter set every time)

@@ -143,3 +143,39 @@ def test_oracle_against_live_reference():
     yr, ir = ref_pool(x)
     yo, io = O.maxval_pool(ref_pool.remap_matrix, x)
     assert torch.equal(yr, yo) and torch.equal(ir, io)
+
+
+# ----------------------------------------------------------------------------------------------
+# Training-loop loss: oracle restatement against the unmodified reference
+# ----------------------------------------------------------------------------------------------
+
+
+def test_weighted_mse_oracle_matches_reference_golden():
+    from oracle import loss_oracle as LO
+
+    g = golden("wmse")
+    for tag in ("a", "b"):
+        w = torch.from_numpy(g[f"{tag}_w"])
+        label = torch.from_numpy(g[f"{tag}_label"])
+        for red in ("mean", "sum", "none"):
+            for use_w in (True, False):
+                pred = torch.from_numpy(g[f"{tag}_pred"]).requires_grad_(True)
+                key = f"{tag}_{red}_{'w' if use_w else 'u'}"
+                val = LO.weighted_mse(pred, label, w if use_w else None, red)
+                assert rel_err(val, g[key]) < 1e-6, key
+                if red != "none":
+                    val.backward()
+                    assert rel_err(pred.grad, g[key + "_grad"]) < 1e-6, key
+    y = torch.from_numpy(g["reshape_in"])
+    assert torch.equal(LO.reshape_4_loss(y, ["sample", "time", "node", "feature"]), torch.from_numpy(g["reshape_out"]))
+    with pytest.raises(ValueError):
+        LO.weighted_mse(torch.zeros(1, 4, 1), torch.zeros(1, 4, 1), torch.ones(3))
+
+
+def test_reshape_tensors_4_loss_matches_reference_golden():
+    from deepsphere_weather_b200.losses import reshape_tensors_4_loss
+
+    g = golden("wmse")
+    y = torch.from_numpy(g["reshape_in"])
+    a, b = reshape_tensors_4_loss(y, y + 1, {"sample": 0, "time": 1, "node": 2, "feature": 3})
+    assert torch.equal(a, torch.from_numpy(g["reshape_out"])) and torch.equal(b, a + 1)
