@@ -2,7 +2,7 @@
 
 There is no CPU fallback: if the library is missing, or a call is made with a non-CUDA tensor,
 the product raises.  (``include/dsw.h`` is the authoritative declaration; the argtypes below
-mirror it one to one and ``tests/test_abi.py`` checks that every declared symbol is exported.)
+mirror it one to one and ``tests/test_abi_and_ddp.py`` checks that every declared symbol is exported.)
 """
 from __future__ import annotations
 
@@ -68,6 +68,7 @@ SIGNATURES = {
     "dsw_get_mix_mode": (C.c_int, []),
     "dsw_debug_counters": (C.c_int, [_ptr, C.c_int]),
     "dsw_debug_dense_counters": (C.c_int, [_ptr, C.c_int]),
+    "dsw_debug_chain_counters": (C.c_int, [_ptr, C.c_int]),
     "dsw_set_option": (C.c_int, [C.c_int, _i64]),
     "dsw_get_option": (_i64, [C.c_int]),
 }

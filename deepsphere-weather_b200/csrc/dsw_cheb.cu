@@ -91,9 +91,9 @@ static int32_t conv_chunk(int32_t B, int32_t V, int32_t Fin, int32_t Fout, int32
 static int run_terms(const dsw_csr& A, const dsw_rb& rb, const float* x, int64_t x_sB, int64_t x_sV, float* terms,
                      int64_t plane, int32_t Bc, int32_t F, int32_t K, cudaStream_t st) {
   const int64_t V = A.n_rows;
+  ChainHop hops[DSW_MAX_K];
   for (int k = 1; k < K; ++k) {
-    HopArgs a;
-    a.B = Bc, a.F = F;
+    ChainHop& a = hops[k - 1];
     a.O = terms + (k - 1) * plane, a.o_sB = V * F, a.o_sV = F;
     if (k == 1) {
       a.X = x, a.x_sB = x_sB, a.x_sV = x_sV;
@@ -106,9 +106,8 @@ static int run_terms(const dsw_csr& A, const dsw_rb& rb, const float* x, int64_t
         a.Z = terms + (k - 3) * plane, a.z_sB = V * F, a.z_sV = F;
       }
     }
-    DSW_TRY(launch_hop(A, rb, a, st));
   }
-  return DSW_OK;
+  return launch_hop_chain(A, rb, hops, K - 1, Bc, F, st);
 }
 
 // Clenshaw recurrence under operator A, in place on the K planes G ([K][plane], F channels):
@@ -116,18 +115,18 @@ static int run_terms(const dsw_csr& A, const dsw_rb& rb, const float* x, int64_t
 static int run_clenshaw(const dsw_csr& A, const dsw_rb& rb, float* G, int64_t plane, float* out, int32_t Bc, int32_t F,
                         int32_t K, cudaStream_t st, int32_t act = 0) {
   const int64_t V = A.n_rows, sB = V * F, sV = F;
+  ChainHop hops[DSW_MAX_K];
+  int n = 0;
   for (int k = K - 2; k >= 0; --k) {
-    HopArgs a;
-    a.B = Bc, a.F = F;
+    ChainHop& a = hops[n++];
     a.X = G + (k + 1) * plane, a.x_sB = sB, a.x_sV = sV;
     if (k + 2 <= K - 1) a.Z = G + (k + 2) * plane, a.z_sB = sB, a.z_sV = sV, a.beta = -1.f;
     a.G = G + k * plane, a.g_sB = sB, a.g_sV = sV;
     a.alpha = (k == 0) ? 1.f : 2.f;
     a.O = (k == 0) ? out : G + k * plane, a.o_sB = sB, a.o_sV = sV;
     a.act = (k == 0) ? act : 0;  // the activation follows the last hop
-    DSW_TRY(launch_hop(A, rb, a, st));
   }
-  return DSW_OK;
+  return launch_hop_chain(A, rb, hops, n, Bc, F, st);
 }
 
 // ---- weight-gradient geometry shared by the workspace queries and the calls ----

@@ -10,6 +10,10 @@
 
 #define DSW_TILE_BLOCKS 16
 #define HOP_CNT_SLOTS 64
+#define DSW_PANEL_PAD 4        // zero entry steps appended to every tile's panels (the software pipeline over-reads)
+#define DSW_CHAIN_SETS 8       // rotating sets of chain-kernel sync words (claim counter, epoch, tile flags)
+#define DSW_CHAIN_HDR 16       // ints in front of the flags of a set: [0] claim, [1] CTAs gone, [2] epoch
+#define DSW_CHAIN_MAX_DEPS 32  // a tile may gather from at most this many tiles for the fused chain kernel
 
 struct dsw_csr {
   int32_t n_rows = 0, n_cols = 0;
@@ -48,7 +52,7 @@ struct dsw_rb {
   // row-block of the tile is padded to the tile's longest union with zero weights / offset 0, so the
   // 32 slots of one entry step are contiguous (conflict-free broadcast reads, uniform trip counts).
   int32_t tile_len_max = 0;      // max entry steps of a tile
-  int32_t* tp_ptr = nullptr;     // [n_tiles + 1] cumulative entry steps
+  int32_t* tp_ptr = nullptr;     // [n_tiles + 1] cumulative entry steps (each tile: its longest union + DSW_PANEL_PAD zero steps)
   float4* tp_val = nullptr;      // [total_steps][32] R = 4 weights
   uint32_t* tp_off = nullptr;    // [total_steps][32] byte offset of the source row inside the staged tile (256 B rows)
   // Dynamic item scheduling of the tile hop kernel: HOP_CNT_SLOTS rotating sets of per-tile claim
@@ -56,6 +60,14 @@ struct dsw_rb {
   // set) and the host-side launch counter that picks the set.
   int32_t* hop_cnt = nullptr;               // [HOP_CNT_SLOTS][n_tiles + 1]
   std::atomic<uint32_t>* hop_ring = nullptr;
+  // Fused multi-hop chain kernel (dsw_chain.cu): the tiles a tile gathers from (own tile included) and the
+  // rotating sets of sync words [DSW_CHAIN_SETS][DSW_CHAIN_HDR + chain_flag_cap].
+  int32_t tile_deps_max = 0;     // 0 = chain kernel not available for this operator
+  int32_t* tdep_ptr = nullptr;   // [n_tiles + 1]
+  int32_t* tdep_idx = nullptr;
+  int32_t chain_flag_cap = 0;
+  int32_t* chain_sync = nullptr;
+  std::atomic<uint32_t>* chain_ring = nullptr;
   int32_t* perm = nullptr;     // locality permutation: original row of permuted position p ([n_blocks * R], -1 = padding) or null
   int32_t* blkptr = nullptr;   // [n_blocks + 1] offsets into ucol / uval panels
   int32_t* ucol = nullptr;     // [total_union]
@@ -126,6 +138,22 @@ struct HopArgs {
   int32_t act = 0;           // 1 = ReLU on the result (the last hop of a fused conv + activation)
 };
 int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_t st);
+
+// ---- chain of hops: hop j gathers from hop j-1's output (dsw_chain.cu) ---------------------------------
+// One persistent launch walks all hops in an L2-resident order when the operator's plan supports it; otherwise
+// the hops are launched one by one.  Z / G of hop j may be external or the output of an earlier hop of the chain.
+#define DSW_CHAIN_MAX_HOPS 7
+struct ChainHop {
+  const float* X = nullptr;
+  const float* Z = nullptr;
+  const float* G = nullptr;
+  float* O = nullptr;
+  int64_t x_sB = 0, x_sV = 0, z_sB = 0, z_sV = 0, g_sB = 0, g_sV = 0, o_sB = 0, o_sV = 0;
+  float alpha = 1.f, beta = 0.f;
+  int32_t act = 0;
+  int32_t dep = 0;  // set by the launcher: 1 = wait for the previous hop's tiles
+};
+int launch_hop_chain(const dsw_csr& A, const dsw_rb& rb, const ChainHop* hops, int n, int32_t B, int32_t F, cudaStream_t st);
 
 // ---- dense channel mix (CUDA-core fp32) -----------------------------------------------------------
 // C[n][c] = bias[c] + sum_p sum_kk A_p[n][kk] * Bm[p*sBp + kk*sBk + (c/Cw)*sBc1 + (c%Cw)*sBc0]

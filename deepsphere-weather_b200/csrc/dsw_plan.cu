@@ -85,6 +85,8 @@ struct HostRb {
   std::vector<int32_t> tp_ptr;
   std::vector<float> tp_val;      // 4 floats per (step, slot)
   std::vector<uint32_t> tp_off;
+  int32_t tile_deps_max = 0;
+  std::vector<int32_t> tdep_ptr, tdep_idx;
 };
 
 static void build_tiles(HostRb& rb) {
@@ -140,15 +142,33 @@ static void build_tiles(HostRb& rb) {
     for (int32_t b = b0; b < b1; ++b) len = std::max(len, rb.blkptr[b + 1] - rb.blkptr[b]);
     rb.tile_len_max = std::max(rb.tile_len_max, len);
     const size_t base = static_cast<size_t>(rb.tp_ptr[t]) * DSW_TILE_BLOCKS;
-    rb.tp_val.resize((base + static_cast<size_t>(len) * DSW_TILE_BLOCKS) * 4, 0.f);
-    rb.tp_off.resize(base + static_cast<size_t>(len) * DSW_TILE_BLOCKS, 0u);
+    // the tile's panels end with DSW_PANEL_PAD all-zero steps, so that one bulk copy stages them ready to use
+    rb.tp_val.resize((base + static_cast<size_t>(len + DSW_PANEL_PAD) * DSW_TILE_BLOCKS) * 4, 0.f);
+    rb.tp_off.resize(base + static_cast<size_t>(len + DSW_PANEL_PAD) * DSW_TILE_BLOCKS, 0u);
     for (int32_t b = b0; b < b1; ++b)
       for (int32_t e = rb.blkptr[b], u = 0; e < rb.blkptr[b + 1]; ++e, ++u) {
         const size_t at = base + static_cast<size_t>(u) * DSW_TILE_BLOCKS + (b - b0);
         for (int r = 0; r < 4; ++r) rb.tp_val[at * 4 + r] = rb.uval[static_cast<size_t>(e) * 4 + r];
         rb.tp_off[at] = static_cast<uint32_t>(rb.lidx[e]) * 256u;
       }
-    rb.tp_ptr[t + 1] = rb.tp_ptr[t] + len;
+    rb.tp_ptr[t + 1] = rb.tp_ptr[t] + len + DSW_PANEL_PAD;
+  }
+  // Tile dependencies of the fused chain kernel: tile t of hop k may start once hop k-1 has finished every tile
+  // that holds one of t's source rows (square operators in natural order only; own tile always included).
+  rb.tdep_ptr.assign(static_cast<size_t>(rb.n_tiles) + 1, 0);
+  if (rb.perm.empty()) {
+    const int32_t rows_per_tile = 4 * DSW_TILE_BLOCKS;
+    std::vector<int32_t> deps;
+    for (int32_t t = 0; t < rb.n_tiles; ++t) {
+      deps.clear();
+      deps.push_back(t);
+      for (int32_t i = rb.tile_ptr[t]; i < rb.tile_ptr[t + 1]; ++i) deps.push_back(rb.tile_row[i] / rows_per_tile);
+      std::sort(deps.begin(), deps.end());
+      deps.erase(std::unique(deps.begin(), deps.end()), deps.end());
+      rb.tdep_idx.insert(rb.tdep_idx.end(), deps.begin(), deps.end());
+      rb.tdep_ptr[t + 1] = static_cast<int32_t>(rb.tdep_idx.size());
+      rb.tile_deps_max = std::max<int32_t>(rb.tile_deps_max, static_cast<int32_t>(deps.size()));
+    }
   }
 }
 
@@ -329,7 +349,7 @@ static cudaError_t upload_csr(dsw_csr* d, const HostCsr& h, cudaStream_t st) {
   return upload(&d->val, h.val, st);
 }
 
-static cudaError_t upload_rb(dsw_rb* d, const HostRb& h, cudaStream_t st) {
+static cudaError_t upload_rb(dsw_rb* d, const HostRb& h, cudaStream_t st, bool square) {
   d->R = h.R;
   d->n_blocks = h.n_blocks;
   d->max_union = h.max_union;
@@ -362,6 +382,17 @@ static cudaError_t upload_rb(dsw_rb* d, const HostRb& h, cudaStream_t st) {
     if ((e = cudaMalloc(reinterpret_cast<void**>(&d->hop_cnt), cnt_bytes)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(d->hop_cnt, 0, cnt_bytes, st)) != cudaSuccess) return e;
     d->hop_ring = new std::atomic<uint32_t>(0);
+    // fused chain kernel: dependency lists + sync words (square operators whose tiles gather from few tiles)
+    if (h.tile_deps_max > 0 && h.tile_deps_max <= DSW_CHAIN_MAX_DEPS && square) {
+      if ((e = upload(&d->tdep_ptr, h.tdep_ptr, st)) != cudaSuccess) return e;
+      if ((e = upload(&d->tdep_idx, h.tdep_idx, st)) != cudaSuccess) return e;
+      d->tile_deps_max = h.tile_deps_max;
+      d->chain_flag_cap = std::max(64 * h.n_tiles, 32768);
+      const size_t words = (size_t)DSW_CHAIN_SETS * (DSW_CHAIN_HDR + (size_t)d->chain_flag_cap);
+      if ((e = cudaMalloc(reinterpret_cast<void**>(&d->chain_sync), words * sizeof(int32_t))) != cudaSuccess) return e;
+      if ((e = cudaMemsetAsync(d->chain_sync, 0, words * sizeof(int32_t), st)) != cudaSuccess) return e;
+      d->chain_ring = new std::atomic<uint32_t>(0);
+    }
   }
   return cudaSuccess;
 }
@@ -388,6 +419,10 @@ static void free_rb(dsw_rb* r) {
   cudaFree(r->perm);
   cudaFree(r->hop_cnt);
   delete r->hop_ring;
+  cudaFree(r->tdep_ptr);
+  cudaFree(r->tdep_idx);
+  cudaFree(r->chain_sync);
+  delete r->chain_ring;
   *r = dsw_rb{};
 }
 
@@ -472,11 +507,11 @@ int dsw_plan_create(int32_t n_rows, int32_t n_cols, int64_t nnz, const int64_t* 
   if (e == cudaSuccess) e = upload_csr(&p->tr, tr, st);
   if (e == cudaSuccess) {
     const int32_t rf = pick_rb_rows(fwd);
-    if (rf > 0) e = upload_rb(&p->fwd_rb, build_rb_auto(fwd, rf), st);
+    if (rf > 0) e = upload_rb(&p->fwd_rb, build_rb_auto(fwd, rf), st, n_rows == n_cols);
   }
   if (e == cudaSuccess) {
     const int32_t rt = pick_rb_rows(tr);
-    if (rt > 0) e = upload_rb(&p->tr_rb, build_rb_auto(tr, rt), st);
+    if (rt > 0) e = upload_rb(&p->tr_rb, build_rb_auto(tr, rt), st, n_rows == n_cols);
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // host vectors go out of scope
   if (e != cudaSuccess) {

@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) hop_tile_kernel(const int32_t
 // group XOR parity), which keeps the 128-bit reads bank-conflict free.
 // ---------------------------------------------------------------------------------------------
 constexpr int MAX_TEAMS = 5;
-constexpr int PANEL_PAD = 4;        // zero entry steps appended so that the pipeline may over-read
+constexpr int PANEL_PAD = DSW_PANEL_PAD;  // zero entry steps appended so that the pipeline may over-read
 
 struct TeamHopPlan {
   const int32_t* blkptr;
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
   const int tile = blockIdx.x;
   const int blk0 = tile * DSW_TILE_BLOCKS;
   const int t0 = __ldg(P.tp_ptr + tile);
-  const int len = __ldg(P.tp_ptr + tile + 1) - t0;
+  const int len = __ldg(P.tp_ptr + tile + 1) - t0 - PANEL_PAD;  // the plan's panels carry the pad steps
   const int r0 = __ldg(P.tile_ptr + tile);
   const int nrows = __ldg(P.tile_ptr + tile + 1) - r0;
   // Programmatic dependent launch: the next kernel of the stream may start its CTAs (plan staging only) as

@@ -260,7 +260,11 @@ enum {
   DSW_OPT_HOP_PREFETCH = 14,  /* the hop kernel L2-prefetches the next item's Z / G rows when it issues its tile transfer (default); 2 = off */
   DSW_OPT_NO_PDL = 15,        /* 1 = launch the hop kernel without programmatic stream serialisation */
   DSW_OPT_PLAN_PERMUTE = 16,  /* locality permutation of the row-block layout at plan creation: 0 = automatic, 1 = never, 2 = always */
-  DSW_OPT_COUNT = 17
+  DSW_OPT_NO_CHAIN = 17,      /* 1 = launch the hops of a recurrence one by one instead of the fused persistent chain kernel */
+  DSW_OPT_CHAIN_L2_BYTES = 18, /* L2 budget (bytes) for the three live planes of a sample group of the chain kernel; 0 = default 64 MiB */
+  DSW_OPT_CHAIN_MIN_PASS = 19, /* least number of work items of one hop pass of the chain kernel; 0 = default 2 x teams in flight */
+  DSW_OPT_CHAIN_MIN_HOPS = 20, /* chains shorter than this many hops are launched hop by hop; 0 / 1 = every chain is fused */
+  DSW_OPT_COUNT = 21
 };
 /* Tuning only: with DSW_OPT_DEBUG = 4 the hop kernel sums per-phase SM cycles over its teams
  * (issue staging, wait for tile + Z/G, entry loop, stores, item count). */
@@ -268,6 +272,9 @@ int dsw_debug_counters(uint64_t* out8, int reset);
 /* Tuning only: with DSW_OPT_DEBUG bit 512 the weight-gradient kernel sums role cycles over its CTAs (converters
  * waiting for the TMA, converting, stage count, producer waiting for a free stage, MMA issuer waiting). */
 int dsw_debug_dense_counters(uint64_t* out8, int reset);
+/* Tuning only: with DSW_OPT_DEBUG = 4 the fused chain kernel sums per-phase SM cycles over its teams
+ * (Z/G loads, wait for the transfers, entry loop, stores + flag + next staging, item count). */
+int dsw_debug_chain_counters(uint64_t* out8, int reset);
 int dsw_set_option(int key, int64_t value);
 int64_t dsw_get_option(int key);
 
