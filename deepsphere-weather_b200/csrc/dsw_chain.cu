@@ -8,21 +8,28 @@
 //
 //   work item  = (sample group g, hop j, tile t, sample s of the group, 64-channel slab)
 //   claim order = that tuple in lexicographic order, taken from ONE global counter by the teams of a persistent
-//                 grid (one CTA per SM, CH_TEAMS independent 64-thread teams per CTA)
+//                 grid (one CTA per SM, CH_TEAMS independent teams per CTA)
 //   group size  = as many samples as keep three planes of the group (gather source, the k-2 term, the output)
 //                 inside the L2 budget, but enough for a hop pass to hold more items than are in flight.
 //
 // Dependencies instead of grid barriers: item (b, j, t) gathers rows of O_{j-1} that lie in a fixed, small set of
-// tiles deps(t) (plan: tdep_ptr / tdep_idx, own tile included).  Every finished item publishes
-// flag[b][slab][t] = epoch * 16 + j + 1 (release); an item polls the flags of its deps (acquire) before it issues
-// its transfers.  Claims are handed out in order and an item only ever waits for smaller claims, so the grid
-// cannot deadlock whatever its size.  The epoch lives in device memory and is bumped by the last CTA to leave,
-// which also zeroes the claim counter: no memset launches, and captured CUDA graphs replay correctly.
+// tiles deps(t) (plan: tdep_fix, own tile included).  Every finished item publishes
+// flag[b][slab][t] = epoch * 16 + j + 1 behind a gpu-scope release; an item's flags are polled before its transfers
+// are issued.  Claims are handed out in order and an item only ever waits for smaller claims, so the grid cannot
+// deadlock whatever its size.  The epoch lives in device memory and is bumped by the last CTA to leave, which also
+// zeroes the claim counter: no memset launches, and captured CUDA graphs replay correctly.
 //
-// Per item a team stages, with one mbarrier: the tile's entry-major weight / offset panels (two bulk copies) and
-// the distinct source rows the tile gathers (one tensor-map box per run of consecutive rows).  The arithmetic is
-// the register-tiled loop of hop_team_kernel (dsw_spmm.cu): 4 lanes own a row-block of 4 rows x 64 channels,
-// every 16-byte shared-memory read feeds 4 packed FMAs.
+// Warp roles (512 threads, registers rebalanced with setmaxnreg):
+//   warps 0-7   four compute teams of two warps.  4 lanes own a row-block of 4 rows x 64 channels (64 fp32
+//               accumulators per lane); every 16-byte shared-memory read feeds 4 packed FMAs (FFMA2) — the
+//               register-tiled loop of hop_team_kernel (dsw_spmm.cu).  They only ever wait on mbarriers.
+//   warps 8-11  one issuer warp per team, running one item ahead of it: claim, decode, the tile's metadata (one
+//               round trip: fixed-stride plan tables), dependency flags (a second one); the moment the team's
+//               entry loop ends it issues the transfers — the tile's weight / offset panels (two bulk copies) and the
+//               distinct source rows the tile gathers (one tensor-map box per run of consecutive rows).
+//   warp 12     publisher: collects the items whose stores have been issued and releases their flags behind ONE
+//               gpu-scope fence per round (a MEMBAR.ALL.GPU costs ~7k cycles on a busy SM: it must not sit on a
+//               compute or issuer warp's path).
 #include <algorithm>
 
 #include "dsw_internal.cuh"
@@ -31,20 +38,21 @@
 namespace dsw {
 
 constexpr int CH_TEAMS = 4;
-constexpr int CH_TEAM_THREADS = DSW_TILE_BLOCKS * 4;  // 4 lanes per row-block
-constexpr int CH_THREADS = CH_TEAMS * CH_TEAM_THREADS;
+constexpr int CH_TEAM_THREADS = DSW_TILE_BLOCKS * 4;  // 4 lanes per row-block: two compute warps per team
+constexpr int CH_COMPUTE_THREADS = CH_TEAMS * CH_TEAM_THREADS;
+constexpr int CH_THREADS = 512;                       // 8 compute warps, 4 issuer warps, publisher + 3 idle warps
+constexpr int CH_DESC_RING = 4;                       // item descriptors per team
+constexpr int CH_REGS_COMPUTE = 200, CH_REGS_ISSUER = 64, CH_REGS_PUBLISHER = 40;
 
 struct ChainPlan {
   const int32_t* blkptr;
   const int32_t* tp_ptr;
   const float4* tp_val;
   const uint32_t* tp_off;
-  const int32_t* tile_ptr;
-  const int32_t* tpc_ptr;
-  const int32_t* tpc_row;
-  const uint32_t* tpc_meta;
-  const int32_t* tdep_ptr;
-  const int32_t* tdep_idx;
+  const int4* tile_meta;
+  const int2* tpc_fix;
+  const int32_t* tdep_fix;
+  int32_t pieces_stride, deps_stride;
   int32_t n_blocks, n_rows, n_tiles, cap_len, cap_rows;
   int32_t n_hops, n_slabs, F;
   int32_t S, S_last, n_full_groups;  // samples per group, samples of the ragged last group (0 = none)
@@ -64,7 +72,7 @@ struct ChainMaps {
   CUtensorMap m[DSW_CHAIN_MAX_HOPS][8];  // box rows 1, 2, 4, .. 128 over hop j's gather source [B][V][F]
 };
 
-__device__ unsigned long long g_chain_prof[8];
+__device__ unsigned long long g_chain_prof[16];  // [0..7] compute teams, [8..15] control warps
 
 namespace {
 
@@ -93,16 +101,27 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ int32_t ld_acquire(const int32_t* p) {
+// Dependency flags are polled with a strong relaxed load.  What is read once a flag is seen — the source rows (TMA)
+// and the Z / G rows (ld.global.cg) — is fetched from L2, the point of coherence, where the producer's gpu-scope
+// release (MEMBAR.ALL.GPU before the flag store) has put it; no L1 line is involved, so the L1 invalidation an
+// acquire load would cost the whole SM on every poll (CCTL.IVALL) buys nothing here.
+__device__ __forceinline__ int32_t ld_flag(const int32_t* p) {
   int32_t v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release(int32_t* p, int32_t v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void team_bar(int team) {
-  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(CH_TEAM_THREADS) : "memory");
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
 }
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void fma4(float4& acc, float w, const float4& x) {
@@ -121,12 +140,46 @@ __device__ __forceinline__ void fma_step(float4 (&acc)[4][4], const float4& w, c
   }
 }
 
-// What a team needs to know about its current item (written by the team's lane 0, read after a team barrier).
+// What a team needs to know about its current item (written by its issuer warp, read after the `ready` barrier).
 struct ItemDesc {
-  int32_t idx;   // claim index (>= total_items: nothing left)
+  int32_t idx;   // claim index (< 0: nothing left, leave)
   int32_t hop, tile, b, slab;
   int32_t pad[3];
 };
+
+// mbarriers of one team
+struct TeamBars {
+  uint64_t ready;  // issuer -> team: descriptor written, dependencies met, transfers issued (count 1)
+  uint64_t full;   // transfers -> team: rows and panels have landed (count 1 + tx bytes)
+  uint64_t empty;  // team -> issuer: the entry loop is over, the buffers may be overwritten (count 2: one lane per warp)
+};
+
+// plain words shared between the roles of one team
+struct TeamWords {
+  uint32_t done[2];    // per compute warp: items whose stores have been issued (release, cta)
+  uint32_t published;  // items whose flag is out (publisher)
+  int32_t total;       // items the issuer handed to the team, -1 while it is still claiming
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void red_release_cta(uint32_t* p) {
+  asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(p)) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cta(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_volatile_s(const void* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_s(void* p, uint32_t v) {
+  asm volatile("st.volatile.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
 
 }  // namespace
 
@@ -134,23 +187,22 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     hop_chain_kernel(const ChainPlan P, const __grid_constant__ ChainArgs A, const __grid_constant__ ChainMaps maps) {
   extern __shared__ __align__(1024) uint8_t ch_smem[];
   const int tid = threadIdx.x;
-  const int team = tid / CH_TEAM_THREADS;
-  const int tt = tid - team * CH_TEAM_THREADS;
+  const int warp = tid >> 5, lane = tid & 31;
 
-  // shared memory: [team 0: rows | weights | offsets] ... [team 3] | mbarriers | item descriptors | epoch
-  uint8_t* xs = ch_smem + (size_t)team * P.team_stride;
-  const int cap_steps = P.cap_len + DSW_PANEL_PAD;
-  const float4* s_val = reinterpret_cast<const float4*>(xs + (size_t)P.cap_rows * 256);
-  const uint32_t* s_off = reinterpret_cast<const uint32_t*>(xs + (size_t)P.cap_rows * 256 + (size_t)cap_steps * DSW_TILE_BLOCKS * 16);
+  // shared memory: [team 0: rows | weights | offsets] ... [team 3] | mbarriers | words | item descriptors | epoch
   uint8_t* tail = ch_smem + (size_t)CH_TEAMS * P.team_stride;
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(tail);
-  ItemDesc* s_item = reinterpret_cast<ItemDesc*>(tail + 64);
-  int32_t* s_epoch = reinterpret_cast<int32_t*>(tail + 64 + CH_TEAMS * sizeof(ItemDesc));
-  const uint32_t xs_u32 = smem_u32(xs);
-  const uint32_t bar = smem_u32(s_bar + team);
+  TeamBars* s_bars = reinterpret_cast<TeamBars*>(tail);
+  TeamWords* s_words = reinterpret_cast<TeamWords*>(tail + CH_TEAMS * sizeof(TeamBars));
+  ItemDesc* s_item = reinterpret_cast<ItemDesc*>(tail + CH_TEAMS * (sizeof(TeamBars) + sizeof(TeamWords)));
+  int32_t* s_epoch = reinterpret_cast<int32_t*>(tail + CH_TEAMS * (sizeof(TeamBars) + sizeof(TeamWords) + CH_DESC_RING * sizeof(ItemDesc)));
 
   pdl_trigger();
-  if (tid < CH_TEAMS) mbar_init(smem_u32(s_bar + tid), 1);
+  if (tid < CH_TEAMS) {
+    mbar_init(smem_u32(&s_bars[tid].ready), 1);
+    mbar_init(smem_u32(&s_bars[tid].full), 1);
+    mbar_init(smem_u32(&s_bars[tid].empty), CH_TEAM_THREADS / 32);
+    s_words[tid].done[0] = 0, s_words[tid].done[1] = 0, s_words[tid].published = 0, s_words[tid].total = -1;
+  }
   if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   // everything the previous kernel of the stream wrote (operands, and — if the ring of sets has wrapped — this set's
   // sync words) is visible from here on
@@ -161,216 +213,309 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
   int32_t* const claim = P.sync;
   int32_t* const flags = P.sync + DSW_CHAIN_HDR;
 
-  // ---- staging (the team's first warp) ----
-  // Decodes the claim, waits (or just checks) for the tiles the item gathers from, then issues the transfers.
-  // Returns false when `blocking` is false and a dependency is still open (nothing issued then).
-  auto stage = [&](int32_t idx, bool blocking) -> bool {
-    int32_t g, r, Sg;
-    if (idx < P.n_full_groups * P.items_full) {
-      g = idx / P.items_full, r = idx - g * P.items_full, Sg = P.S;
-    } else {
-      g = P.n_full_groups, r = idx - g * P.items_full, Sg = P.S_last;
+  if (warp >= 12) {
+    // ========================================= publisher =========================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CH_REGS_PUBLISHER));
+    if (warp == 12) {
+      uint32_t pn = 0;  // lane t < CH_TEAMS: items of team t published so far
+      bool finished = lane >= CH_TEAMS;
+      while (true) {
+        uint32_t avail = 0;
+        if (!finished) {
+          avail = min(ld_acquire_cta(&s_words[lane].done[0]), ld_acquire_cta(&s_words[lane].done[1]));
+          const int32_t total = (int32_t)ld_volatile_s(&s_words[lane].total);
+          if (total >= 0 && pn == (uint32_t)total) finished = true;
+        }
+        const bool mine = !finished && avail > pn;
+        if (__any_sync(0xffffffffu, mine)) {
+          // one gpu-scope release for every item collected this round: the teams' stores (ordered before `done` at cta
+          // scope) reach L2 before any of the flags below does
+          __threadfence();
+          if (mine) {
+            for (; pn < avail; ++pn) {
+              const ItemDesc* d = &s_item[lane * CH_DESC_RING + (pn % CH_DESC_RING)];
+              const int32_t hop = (int32_t)ld_volatile_s(&d->hop), tile = (int32_t)ld_volatile_s(&d->tile);
+              const int32_t b = (int32_t)ld_volatile_s(&d->b), slab = (int32_t)ld_volatile_s(&d->slab);
+              asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(flags + ((int64_t)b * P.n_slabs + slab) * P.n_tiles + tile),
+                           "r"(base + hop + 1)
+                           : "memory");
+            }
+            st_volatile_s(&s_words[lane].published, pn);
+          }
+        } else if (__all_sync(0xffffffffu, finished)) {
+          break;
+        } else {
+          __nanosleep(40);
+        }
+      }
     }
-    const int32_t per_tile = Sg * P.n_slabs, per_hop = P.n_tiles * per_tile;
-    const int32_t hop = r / per_hop;
-    r -= hop * per_hop;
-    const int32_t tile = r / per_tile;
-    r -= tile * per_tile;
-    const int32_t s = r / P.n_slabs, slab = r - s * P.n_slabs;
-    const int32_t b = g * P.S + s;
-    const ChainHop& H = A.h[hop];
-    if (H.dep) {
-      const int32_t d0 = __ldg(P.tdep_ptr + tile), nd = __ldg(P.tdep_ptr + tile + 1) - d0;
-      const int32_t* f = flags + ((int64_t)b * P.n_slabs + slab) * P.n_tiles;
-      const int32_t need = base + hop;  // hop - 1 finished
-      const int32_t dep = tt < nd ? __ldg(P.tdep_idx + d0 + tt) : -1;
-      bool ok = dep < 0 || ld_acquire(f + dep) - need >= 0;
-      if (!blocking) {
-        if (!__all_sync(0xffffffffu, ok)) return false;
+  } else if (warp >= CH_COMPUTE_THREADS / 32) {
+    // ========================================== issuer ===========================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CH_REGS_ISSUER));
+    const int team = warp - CH_COMPUTE_THREADS / 32;
+    uint8_t* xs = ch_smem + (size_t)team * P.team_stride;
+    const uint32_t xs_u32 = smem_u32(xs);
+    const uint32_t sval_u32 = xs_u32 + (uint32_t)P.cap_rows * 256u;
+    const uint32_t soff_u32 = sval_u32 + (uint32_t)(P.cap_len + DSW_PANEL_PAD) * DSW_TILE_BLOCKS * 16u;
+    const uint32_t bar_ready = smem_u32(&s_bars[team].ready), bar_full = smem_u32(&s_bars[team].full);
+    const uint32_t bar_empty = smem_u32(&s_bars[team].empty);
+    const bool cprof = (P.debug_skip & 4) && (lane == 0);
+
+    int32_t idx = 0;
+    if (lane == 0) idx = atomicAdd(claim, 1);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    for (uint32_t n = 0;; ++n) {
+      long long k0 = 0, k1 = 0, k2 = 0, k3 = 0;
+      if (cprof) k0 = clock64();
+      if (idx >= P.total_items) {
+        // nothing left: the team leaves after its current item, the publisher after the team's last flag
+        if (n > 0) mbar_wait(bar_empty, (n - 1) & 1u);
+        while (n >= CH_DESC_RING && ld_volatile_s(&s_words[team].published) + CH_DESC_RING <= n) __nanosleep(40);
+        if (lane == 0) {
+          st_volatile_s(&s_item[team * CH_DESC_RING + (n % CH_DESC_RING)].idx, (uint32_t)-1);
+          st_volatile_s(&s_words[team].total, n);
+          mbar_arrive(bar_ready);
+        }
+        break;
+      }
+      int32_t idx_next = 0;
+      const bool claim_ahead = !(P.debug_skip & 32);
+      if (lane == 0 && claim_ahead) idx_next = atomicAdd(claim, 1);  // consumed at the top of the next round
+      // ---- decode item n and fetch its metadata (the team is still busy with item n - 1) ----
+      int32_t g, r, Sg;
+      if (idx < P.n_full_groups * P.items_full) {
+        g = idx / P.items_full, r = idx - g * P.items_full, Sg = P.S;
       } else {
+        g = P.n_full_groups, r = idx - g * P.items_full, Sg = P.S_last;
+      }
+      const int32_t per_tile = Sg * P.n_slabs, per_hop = P.n_tiles * per_tile;
+      const int32_t hop = r / per_hop;
+      r -= hop * per_hop;
+      const int32_t tile = r / per_tile;
+      r -= tile * per_tile;
+      const int32_t s = r / P.n_slabs, slab = r - s * P.n_slabs;
+      const int32_t b = g * P.S + s;
+      // one round trip: tile record, this lane's pieces, this lane's dependency
+      const int4 tm = __ldg(P.tile_meta + 2 * tile);  // {panel step offset, steps, source rows, pieces}
+      int2 pc0 = make_int2(-1, 0), pc1 = make_int2(-1, 0);
+      if (lane < P.pieces_stride) pc0 = __ldg(P.tpc_fix + (size_t)tile * P.pieces_stride + lane);
+      if (lane + 32 < P.pieces_stride) pc1 = __ldg(P.tpc_fix + (size_t)tile * P.pieces_stride + lane + 32);
+      const bool dep = A.h[hop].dep != 0;
+      int32_t dtile = -1;
+      if (dep && lane < P.deps_stride) dtile = __ldg(P.tdep_fix + (size_t)tile * P.deps_stride + lane);
+      const int32_t need = base + hop;  // hop - 1 finished
+      const int32_t* fdep = dtile >= 0 ? flags + ((int64_t)b * P.n_slabs + slab) * P.n_tiles + dtile : nullptr;
+      // a second one: an early look at the dependencies (they are a whole hop pass old and almost always met by now)
+      bool dep_ok = __all_sync(0xffffffffu, fdep == nullptr || ld_flag(fdep) - need >= 0);
+      if (cprof) k1 = clock64();
+
+      // ---- the team's buffers are free once its entry loop of item n - 1 is over ----
+      if (n > 0) mbar_wait(bar_empty, (n - 1) & 1u);
+      if (cprof) k2 = clock64();
+      bool late = false;
+      if (!dep_ok) dep_ok = __all_sync(0xffffffffu, fdep == nullptr || ld_flag(fdep) - need >= 0);
+      if (!dep_ok) {
+        // A blocking wait must not start before every earlier item of this team is published (item n may depend on
+        // them); the team pays its `done` arrival at once when it finds no next item.
+        late = true;
+        while (ld_volatile_s(&s_words[team].published) < n) __nanosleep(40);
+        bool ok = fdep == nullptr || ld_flag(fdep) - need >= 0;
         while (!ok) {
-          __nanosleep(100);
-          ok = ld_acquire(f + dep) - need >= 0;
+          __nanosleep(64);
+          ok = ld_flag(fdep) - need >= 0;
         }
         __syncwarp();
       }
+      // the descriptor slot is free once the publisher is done with item n - CH_DESC_RING
+      while (n >= CH_DESC_RING && ld_volatile_s(&s_words[team].published) + CH_DESC_RING <= n) __nanosleep(40);
+      // the team read the buffers through the generic proxy; the transfers write them through the async proxy
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (lane == 0) {
+        ItemDesc d;
+        d.idx = idx, d.hop = hop, d.tile = tile, d.b = b, d.slab = slab;
+        s_item[team * CH_DESC_RING + (n % CH_DESC_RING)] = d;
+        mbar_expect_tx(bar_full, (uint32_t)tm.z * 256u + (uint32_t)tm.y * (DSW_TILE_BLOCKS * 20u));
+        bulk_g2s(sval_u32, P.tp_val + (size_t)tm.x * DSW_TILE_BLOCKS, (uint32_t)tm.y * (DSW_TILE_BLOCKS * 16u), bar_full);
+        bulk_g2s(soff_u32, P.tp_off + (size_t)tm.x * DSW_TILE_BLOCKS, (uint32_t)tm.y * (DSW_TILE_BLOCKS * 4u), bar_full);
+      }
+      __syncwarp();
+      const CUtensorMap* mp = &maps.m[hop][0];
+      if (pc0.x != -1) tma_load_3d(xs_u32 + ((uint32_t)pc0.x >> 8) * 256u, mp + (pc0.x & 7), slab * 64, pc0.y, b, bar_full);
+      if (pc1.x != -1) tma_load_3d(xs_u32 + ((uint32_t)pc1.x >> 8) * 256u, mp + (pc1.x & 7), slab * 64, pc1.y, b, bar_full);
+      for (int i = lane + 64; i < tm.w; i += 32) {
+        const int2 pc = __ldg(P.tpc_fix + (size_t)tile * P.pieces_stride + i);
+        tma_load_3d(xs_u32 + ((uint32_t)pc.x >> 8) * 256u, mp + (pc.x & 7), slab * 64, pc.y, b, bar_full);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_ready);
+      if (cprof && n > 0) {
+        k3 = clock64();
+        atomicAdd(&g_chain_prof[8], (unsigned long long)(k1 - k0));   // claim, decode, metadata, early dependency look
+        atomicAdd(&g_chain_prof[9], (unsigned long long)(k2 - k1));   // waiting for the team's entry loop to end
+        atomicAdd(&g_chain_prof[10], (unsigned long long)(k3 - k2));  // dependency re-check (+ blocking wait) + issue
+        atomicAdd(&g_chain_prof[14], late ? 1ull : 0ull);             // items whose dependencies were not met in time
+        atomicAdd(&g_chain_prof[15], 1ull);
+      }
+      if (lane == 0 && !claim_ahead) idx_next = atomicAdd(claim, 1);
+      idx = __shfl_sync(0xffffffffu, idx_next, 0);
     }
-    const int32_t t0 = __ldg(P.tp_ptr + tile), steps = __ldg(P.tp_ptr + tile + 1) - t0;
-    const int32_t nrows = __ldg(P.tile_ptr + tile + 1) - __ldg(P.tile_ptr + tile);
-    const int32_t pc0 = __ldg(P.tpc_ptr + tile), npieces = __ldg(P.tpc_ptr + tile + 1) - pc0;
-    // the source rows were written through the generic proxy (by other SMs), the buffer was read through it
-    asm volatile("fence.proxy.async;" ::: "memory");
-    if (tt == 0) {
-      ItemDesc d;
-      d.idx = idx, d.hop = hop, d.tile = tile, d.b = b, d.slab = slab;
-      s_item[team] = d;
-      mbar_expect_tx(bar, (uint32_t)nrows * 256u + (uint32_t)steps * (DSW_TILE_BLOCKS * 20u));
-      bulk_g2s(smem_u32(s_val), P.tp_val + (size_t)t0 * DSW_TILE_BLOCKS, (uint32_t)steps * (DSW_TILE_BLOCKS * 16u), bar);
-      bulk_g2s(smem_u32(s_off), P.tp_off + (size_t)t0 * DSW_TILE_BLOCKS, (uint32_t)steps * (DSW_TILE_BLOCKS * 4u), bar);
-    }
-    __syncwarp();
-    for (int i = tt; i < npieces; i += 32) {
-      const uint32_t meta = __ldg(P.tpc_meta + pc0 + i);
-      tma_load_3d(xs_u32 + (meta >> 8) * 256u, &maps.m[hop][meta & 7u], slab * 64, __ldg(P.tpc_row + pc0 + i), b, bar);
-    }
-    return true;
-  };
+  } else {
+    // ======================================= compute team =======================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CH_REGS_COMPUTE));
+    const int team = tid / CH_TEAM_THREADS;
+    const int tt = tid - team * CH_TEAM_THREADS;
+    const uint8_t* xs = ch_smem + (size_t)team * P.team_stride;
+    const float4* s_val = reinterpret_cast<const float4*>(xs + (size_t)P.cap_rows * 256);
+    const uint32_t* s_off =
+        reinterpret_cast<const uint32_t*>(xs + (size_t)P.cap_rows * 256 + (size_t)(P.cap_len + DSW_PANEL_PAD) * DSW_TILE_BLOCKS * 16);
+    const uint32_t bar_ready = smem_u32(&s_bars[team].ready), bar_full = smem_u32(&s_bars[team].full);
+    const uint32_t bar_empty = smem_u32(&s_bars[team].empty);
+    uint32_t* const done = &s_words[team].done[tt >> 5];
+    const int slot = tt >> 2, lq = tt & 3, par = slot & 1;
+    const uint32_t cA = ((uint32_t)(lq * 16) ^ (uint32_t)(par * 64));
+    const uint32_t cB = ((uint32_t)(lq * 16 + 64) ^ (uint32_t)(par * 64));
+    const uint8_t* xA = xs + cA;
+    const uint8_t* xB = xs + cB;
+    const uint32_t* po = s_off + slot;
+    const float4* pw = s_val + slot;
+    int ch[4];
+    ch[0] = (int)(cA >> 2), ch[1] = (int)(cB >> 2), ch[2] = ch[0] + 32, ch[3] = ch[1] + 32;
 
-  const int slot = tt >> 2, lq = tt & 3, par = slot & 1;
-  const uint32_t cA = ((uint32_t)(lq * 16) ^ (uint32_t)(par * 64));
-  const uint32_t cB = ((uint32_t)(lq * 16 + 64) ^ (uint32_t)(par * 64));
-  const uint8_t* xA = xs + cA;
-  const uint8_t* xB = xs + cB;
-  const uint32_t* po = s_off + slot;
-  const float4* pw = s_val + slot;
-  int ch[4];
-  ch[0] = (int)(cA >> 2), ch[1] = (int)(cB >> 2), ch[2] = ch[0] + 32, ch[3] = ch[1] + 32;
-
-  // first item
-  int32_t next = P.total_items;  // lane 0 of the team: the claim after the current one
-  if (tt < 32) {
-    int32_t first = 0;
-    if (tt == 0) first = atomicAdd(claim, 1);
-    first = __shfl_sync(0xffffffffu, first, 0);
-    if (first < P.total_items) {
-      stage(first, true);
-    } else if (tt == 0) {
-      s_item[team].idx = first;
-    }
-  }
-  uint32_t phase = 0;
-  while (true) {
-    team_bar(team);  // (A) the descriptor of the current item is visible
-    const ItemDesc d = s_item[team];
-    if (d.idx >= P.total_items) break;
-    if (tt == 0) next = atomicAdd(claim, 1);  // consumed after the entry loop, when the round trip is long over
-    const ChainHop& H = A.h[d.hop];
-    const int blk = d.tile * DSW_TILE_BLOCKS + slot;
-    const bool active = blk < P.n_blocks;
-    const int slab_f = min(64, P.F - d.slab * 64);
-    int my_len = 0;
-    if (active) my_len = __ldg(P.blkptr + blk + 1) - __ldg(P.blkptr + blk);
-    const bool prof = (P.debug_skip == 4) && (tt == 0);
-    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-    if (prof) c0 = clock64();
-
-    // Accumulators start at (beta * Z + G) / alpha (alpha is 1 or 2: exact); the loads land while the tile does.
-    float4 acc[4][4];
-    {
-      const float inv_alpha = 1.f / H.alpha;
-      const float zs = H.beta * inv_alpha;
-      bool ok[4][4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) ok[r][j] = active && (blk * 4 + r) < P.n_rows && ch[j] < slab_f;
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          acc[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (H.Z != nullptr && ok[r][j])
-            acc[r][j] = ldcg4(H.Z + d.b * H.z_sB + (int64_t)(blk * 4 + r) * H.z_sV + d.slab * 64 + ch[j]);
+    for (uint32_t n = 0;; ++n) {
+      const bool prof = (P.debug_skip & 4) && (tt == 0);
+      long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+      if (prof) c0 = clock64();
+      // The `done` arrival of the previous item orders its stores (a CTA-scope memory barrier that waits for them).
+      // If the next item is already there, its Z / G loads go out first and the barrier's wait overlaps the transfers;
+      // otherwise there is nothing better to do than to pay it now (and the issuer may need it before it can wait for
+      // the next item's dependencies).
+      const bool early = n > 0 && __shfl_sync(0xffffffffu, (int)mbar_test(bar_ready, n & 1u), 0) != 0;
+      if (n > 0 && !early) {
+        __syncwarp();
+        if (lane == 0) red_release_cta(done);
+      }
+      mbar_wait(bar_ready, n & 1u);
+      const ItemDesc d = s_item[team * CH_DESC_RING + (n % CH_DESC_RING)];
+      if (d.idx < 0) {
+        if (early) {
+          __syncwarp();
+          if (lane == 0) red_release_cta(done);
         }
+        break;
+      }
+      const ChainHop& H = A.h[d.hop];
+      const int blk = d.tile * DSW_TILE_BLOCKS + slot;
+      const bool active = blk < P.n_blocks;
+      const int slab_f = min(64, P.F - d.slab * 64);
+      int my_len = 0;
+      if (active) my_len = __ldg(P.blkptr + blk + 1) - __ldg(P.blkptr + blk);
+      if (prof) c1 = clock64();
+
+      // Accumulators start at (beta * Z + G) / alpha (alpha is 1 or 2: exact); the loads land while the tile does.
+      float4 acc[4][4];
+      {
+        const float inv_alpha = 1.f / H.alpha;
+        const float zs = H.beta * inv_alpha;
+        bool ok[4][4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          acc[r][j] = make_float4(acc[r][j].x * zs, acc[r][j].y * zs, acc[r][j].z * zs, acc[r][j].w * zs);
-      if (H.G != nullptr) {
-        float4 g[4][4];
+          for (int j = 0; j < 4; ++j) ok[r][j] = active && (blk * 4 + r) < P.n_rows && ch[j] < slab_f;
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            g[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok[r][j]) g[r][j] = ldcg4(H.G + d.b * H.g_sB + (int64_t)(blk * 4 + r) * H.g_sV + d.slab * 64 + ch[j]);
+            acc[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (H.Z != nullptr && ok[r][j] && !(P.debug_skip & 16))
+              acc[r][j] = ldcg4(H.Z + d.b * H.z_sB + (int64_t)(blk * 4 + r) * H.z_sV + d.slab * 64 + ch[j]);
           }
+        if (early && H.G == nullptr) {
+          __syncwarp();
+          if (lane == 0) red_release_cta(done);
+        }
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            acc[r][j] = make_float4(fmaf(g[r][j].x, inv_alpha, acc[r][j].x), fmaf(g[r][j].y, inv_alpha, acc[r][j].y),
-                                    fmaf(g[r][j].z, inv_alpha, acc[r][j].z), fmaf(g[r][j].w, inv_alpha, acc[r][j].w));
-      }
-    }
-    const int wlen = (__reduce_max_sync(0xffffffffu, my_len) + 1) & ~1;
-    if (prof) c1 = clock64();
-    mbar_wait(bar, phase);
-    phase ^= 1u;
-    if (prof) c2 = clock64();
-
-    {
-      auto load_x = [&](uint32_t o, float4(&x)[4]) {
-        x[0] = *reinterpret_cast<const float4*>(xA + o);
-        x[1] = *reinterpret_cast<const float4*>(xB + o);
-        x[2] = *reinterpret_cast<const float4*>(xA + o + 128);
-        x[3] = *reinterpret_cast<const float4*>(xB + o + 128);
-      };
-      // software pipeline: offsets two steps ahead, weights / values one step ahead (the panels end in zero steps)
-      float4 x0[4], x1[4], w0, w1;
-      uint32_t o1, o2;
-      w0 = pw[0];
-      load_x(po[0], x0);
-      o1 = po[DSW_TILE_BLOCKS];
-#pragma unroll 1
-      for (int u = 0; u < (P.debug_skip == 2 ? 0 : wlen); u += 2) {
-        w1 = pw[(u + 1) * DSW_TILE_BLOCKS];
-        load_x(o1, x1);
-        o2 = po[(u + 2) * DSW_TILE_BLOCKS];
-        fma_step(acc, w0, x0);
-        w0 = pw[(u + 2) * DSW_TILE_BLOCKS];
-        load_x(o2, x0);
-        o1 = po[(u + 3) * DSW_TILE_BLOCKS];
-        fma_step(acc, w1, x1);
-      }
-    }
-    team_bar(team);  // (B) every lane is done with the staged rows and panels
-    if (prof) c3 = clock64();
-    // The next item's transfers start now if its dependencies are already met (they almost always are); they then
-    // overlap this item's stores.  A blocking wait must not happen before this item's own flag is out (the next
-    // item may depend on it).
-    bool staged = false;
-    int32_t nxt = 0;
-    if (tt < 32) {
-      nxt = __shfl_sync(0xffffffffu, next, 0);
-      if (nxt < P.total_items) staged = stage(nxt, false);
-    }
-    // ---- epilogue: O = alpha * acc ----
-    if (active) {
+            acc[r][j] = make_float4(acc[r][j].x * zs, acc[r][j].y * zs, acc[r][j].z * zs, acc[r][j].w * zs);
+        if (H.G != nullptr) {
+          float4 g[4][4];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int row = blk * 4 + r;
-        if (row >= P.n_rows) continue;
+          for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (ch[j] >= slab_f) continue;
-          float4 o = make_float4(H.alpha * acc[r][j].x, H.alpha * acc[r][j].y, H.alpha * acc[r][j].z, H.alpha * acc[r][j].w);
-          if (H.act) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
-          *reinterpret_cast<float4*>(H.O + d.b * H.o_sB + (int64_t)row * H.o_sV + d.slab * 64 + ch[j]) = o;
+            for (int j = 0; j < 4; ++j) {
+              g[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ok[r][j]) g[r][j] = ldcg4(H.G + d.b * H.g_sB + (int64_t)(blk * 4 + r) * H.g_sV + d.slab * 64 + ch[j]);
+            }
+          if (early) {
+            __syncwarp();
+            if (lane == 0) red_release_cta(done);
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              acc[r][j] = make_float4(fmaf(g[r][j].x, inv_alpha, acc[r][j].x), fmaf(g[r][j].y, inv_alpha, acc[r][j].y),
+                                      fmaf(g[r][j].z, inv_alpha, acc[r][j].z), fmaf(g[r][j].w, inv_alpha, acc[r][j].w));
         }
       }
-    }
-    team_bar(team);  // (C) every store of the item has been issued
-    if (tt < 32) {
-      if (tt == 0) {
-        __threadfence();
-        st_release(flags + ((int64_t)d.b * P.n_slabs + d.slab) * P.n_tiles + d.tile, base + d.hop + 1);
+      const int wlen = (__reduce_max_sync(0xffffffffu, my_len) + 1) & ~1;
+      mbar_wait(bar_full, n & 1u);
+      if (prof) c2 = clock64();
+
+      {
+        auto load_x = [&](uint32_t o, float4(&x)[4]) {
+          x[0] = *reinterpret_cast<const float4*>(xA + o);
+          x[1] = *reinterpret_cast<const float4*>(xB + o);
+          x[2] = *reinterpret_cast<const float4*>(xA + o + 128);
+          x[3] = *reinterpret_cast<const float4*>(xB + o + 128);
+        };
+        // software pipeline: offsets two steps ahead, weights / values one step ahead (the panels end in zero steps)
+        float4 x0[4], x1[4], w0, w1;
+        uint32_t o1, o2;
+        w0 = pw[0];
+        load_x(po[0], x0);
+        o1 = po[DSW_TILE_BLOCKS];
+#pragma unroll 1
+        for (int u = 0; u < ((P.debug_skip & 2) ? 0 : wlen); u += 2) {
+          w1 = pw[(u + 1) * DSW_TILE_BLOCKS];
+          load_x(o1, x1);
+          o2 = po[(u + 2) * DSW_TILE_BLOCKS];
+          fma_step(acc, w0, x0);
+          w0 = pw[(u + 2) * DSW_TILE_BLOCKS];
+          load_x(o2, x0);
+          o1 = po[(u + 3) * DSW_TILE_BLOCKS];
+          fma_step(acc, w1, x1);
+        }
       }
+      // this warp is done with the staged rows and panels
       __syncwarp();
-      if (nxt < P.total_items) {
-        if (!staged) stage(nxt, true);
-      } else if (tt == 0) {
-        s_item[team].idx = nxt;
+      if (lane == 0) mbar_arrive(bar_empty);
+      if (prof) c3 = clock64();
+      // ---- epilogue: O = alpha * acc ----
+      if (active && !(P.debug_skip & 8)) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int row = blk * 4 + r;
+          if (row >= P.n_rows) continue;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (ch[j] >= slab_f) continue;
+            float4 o = make_float4(H.alpha * acc[r][j].x, H.alpha * acc[r][j].y, H.alpha * acc[r][j].z, H.alpha * acc[r][j].w);
+            if (H.act) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+            *reinterpret_cast<float4*>(H.O + d.b * H.o_sB + (int64_t)row * H.o_sV + d.slab * 64 + ch[j]) = o;
+          }
+        }
       }
-    }
-    if (prof) {
-      const long long c4 = clock64();
-      atomicAdd(&g_chain_prof[0], (unsigned long long)(c1 - c0));  // Z / G loads
-      atomicAdd(&g_chain_prof[1], (unsigned long long)(c2 - c1));  // wait for the transfers
-      atomicAdd(&g_chain_prof[2], (unsigned long long)(c3 - c2));  // entry loop
-      atomicAdd(&g_chain_prof[3], (unsigned long long)(c4 - c3));  // stores, flag, next staging
-      atomicAdd(&g_chain_prof[4], 1ull);
+      // (the `done` arrival follows at the top of the next round)
+      if (prof) {
+        c4 = clock64();
+        atomicAdd(&g_chain_prof[0], (unsigned long long)(c1 - c0));  // wait for the next item (issuer, dependencies)
+        atomicAdd(&g_chain_prof[1], (unsigned long long)(c2 - c1));  // Z / G loads + wait for the transfers
+        atomicAdd(&g_chain_prof[2], (unsigned long long)(c3 - c2));  // entry loop
+        atomicAdd(&g_chain_prof[3], (unsigned long long)(c4 - c3));  // stores
+        atomicAdd(&g_chain_prof[4], 1ull);
+      }
     }
   }
 
@@ -428,15 +573,15 @@ static int launch_chain_fused(const dsw_csr& A, const dsw_rb& rb, const ChainHop
                               cudaStream_t st) {
   ChainPlan P{};
   P.blkptr = rb.blkptr, P.tp_ptr = rb.tp_ptr, P.tp_val = rb.tp_val, P.tp_off = rb.tp_off;
-  P.tile_ptr = rb.tile_ptr, P.tpc_ptr = rb.tpc_ptr, P.tpc_row = rb.tpc_row, P.tpc_meta = rb.tpc_meta;
-  P.tdep_ptr = rb.tdep_ptr, P.tdep_idx = rb.tdep_idx;
+  P.tile_meta = rb.tile_meta, P.tpc_fix = rb.tpc_fix, P.tdep_fix = rb.tdep_fix;
+  P.pieces_stride = rb.tile_pieces_max, P.deps_stride = rb.tile_deps_max;
   P.n_blocks = rb.n_blocks, P.n_rows = A.n_rows, P.n_tiles = rb.n_tiles, P.cap_len = rb.tile_len_max, P.cap_rows = rb.tile_rows_max;
   P.n_hops = n, P.n_slabs = ceil_div(F, 64), P.F = F;
   P.debug_skip = (int)g_options[DSW_OPT_DEBUG].load(std::memory_order_relaxed);
 
   // shared memory per team: staged rows + panels
   const size_t team_bytes = ((size_t)rb.tile_rows_max * 256 + (size_t)(rb.tile_len_max + DSW_PANEL_PAD) * DSW_TILE_BLOCKS * 20 + 127) & ~(size_t)127;
-  const size_t smem = CH_TEAMS * team_bytes + 64 + CH_TEAMS * sizeof(ItemDesc) + 64;
+  const size_t smem = CH_TEAMS * team_bytes + CH_TEAMS * (sizeof(TeamBars) + sizeof(TeamWords) + CH_DESC_RING * sizeof(ItemDesc)) + 64;
   if (smem > 227 * 1024) return DSW_ERR_UNSUPPORTED;
   P.team_stride = (uint32_t)team_bytes;
 
@@ -534,13 +679,13 @@ int launch_hop_chain(const dsw_csr& A, const dsw_rb& rb, const ChainHop* hops, i
 
 }  // namespace dsw
 
-extern "C" int dsw_debug_chain_counters(uint64_t* out8, int reset) {
-  if (!out8) return DSW_ERR_BAD_ARGUMENT;
-  unsigned long long h[8];
+extern "C" int dsw_debug_chain_counters(uint64_t* out16, int reset) {
+  if (!out16) return DSW_ERR_BAD_ARGUMENT;
+  unsigned long long h[16];
   DSW_CUDA_TRY(cudaMemcpyFromSymbol(h, dsw::g_chain_prof, sizeof(h)));
-  for (int i = 0; i < 8; ++i) out8[i] = h[i];
+  for (int i = 0; i < 16; ++i) out16[i] = h[i];
   if (reset) {
-    unsigned long long z[8] = {};
+    unsigned long long z[16] = {};
     DSW_CUDA_TRY(cudaMemcpyToSymbol(dsw::g_chain_prof, z, sizeof(z)));
   }
   return DSW_OK;

@@ -387,6 +387,23 @@ static cudaError_t upload_rb(dsw_rb* d, const HostRb& h, cudaStream_t st, bool s
       if ((e = upload(&d->tdep_ptr, h.tdep_ptr, st)) != cudaSuccess) return e;
       if ((e = upload(&d->tdep_idx, h.tdep_idx, st)) != cudaSuccess) return e;
       d->tile_deps_max = h.tile_deps_max;
+      {
+        std::vector<int4> meta(static_cast<size_t>(h.n_tiles) * 2);
+        std::vector<int2> pcs(static_cast<size_t>(h.n_tiles) * h.tile_pieces_max, make_int2(-1, 0));
+        std::vector<int32_t> deps(static_cast<size_t>(h.n_tiles) * h.tile_deps_max, -1);
+        for (int32_t t = 0; t < h.n_tiles; ++t) {
+          const int32_t np = h.tpc_ptr[t + 1] - h.tpc_ptr[t], nd = h.tdep_ptr[t + 1] - h.tdep_ptr[t];
+          meta[2 * t] = make_int4(h.tp_ptr[t], h.tp_ptr[t + 1] - h.tp_ptr[t], h.tile_ptr[t + 1] - h.tile_ptr[t], np);
+          meta[2 * t + 1] = make_int4(nd, 0, 0, 0);
+          for (int32_t i = 0; i < np; ++i)
+            pcs[static_cast<size_t>(t) * h.tile_pieces_max + i] =
+                make_int2(static_cast<int32_t>(h.tpc_meta[h.tpc_ptr[t] + i]), h.tpc_row[h.tpc_ptr[t] + i]);
+          for (int32_t i = 0; i < nd; ++i) deps[static_cast<size_t>(t) * h.tile_deps_max + i] = h.tdep_idx[h.tdep_ptr[t] + i];
+        }
+        if ((e = upload(&d->tile_meta, meta, st)) != cudaSuccess) return e;
+        if ((e = upload(&d->tpc_fix, pcs, st)) != cudaSuccess) return e;
+        if ((e = upload(&d->tdep_fix, deps, st)) != cudaSuccess) return e;
+      }
       d->chain_flag_cap = std::max(64 * h.n_tiles, 32768);
       const size_t words = (size_t)DSW_CHAIN_SETS * (DSW_CHAIN_HDR + (size_t)d->chain_flag_cap);
       if ((e = cudaMalloc(reinterpret_cast<void**>(&d->chain_sync), words * sizeof(int32_t))) != cudaSuccess) return e;
@@ -421,6 +438,9 @@ static void free_rb(dsw_rb* r) {
   delete r->hop_ring;
   cudaFree(r->tdep_ptr);
   cudaFree(r->tdep_idx);
+  cudaFree(r->tile_meta);
+  cudaFree(r->tpc_fix);
+  cudaFree(r->tdep_fix);
   cudaFree(r->chain_sync);
   delete r->chain_ring;
   *r = dsw_rb{};

@@ -272,9 +272,11 @@ int dsw_debug_counters(uint64_t* out8, int reset);
 /* Tuning only: with DSW_OPT_DEBUG bit 512 the weight-gradient kernel sums role cycles over its CTAs (converters
  * waiting for the TMA, converting, stage count, producer waiting for a free stage, MMA issuer waiting). */
 int dsw_debug_dense_counters(uint64_t* out8, int reset);
-/* Tuning only: with DSW_OPT_DEBUG = 4 the fused chain kernel sums per-phase SM cycles over its teams
- * (Z/G loads, wait for the transfers, entry loop, stores + flag + next staging, item count). */
-int dsw_debug_chain_counters(uint64_t* out8, int reset);
+/* Tuning only: with DSW_OPT_DEBUG = 4 the fused chain kernel sums per-phase SM cycles: [0..4] over its compute
+ * teams (wait for the next item, Z/G loads + wait for the transfers, entry loop, stores, item count), [8..15] over
+ * its control warps (metadata, wait for the loop end, issue, wait for the stores, fence + flag, blocking dependency
+ * wait, items issued late, item count). */
+int dsw_debug_chain_counters(uint64_t* out16, int reset);
 int dsw_set_option(int key, int64_t value);
 int64_t dsw_get_option(int key);
 

@@ -69,9 +69,25 @@ def main():
     lib.dsw_set_option(OPT_L2, 0)
     lib.dsw_set_option(OPT_MIN_PASS, 0)
     lib.dsw_set_option(OPT_NO_CHAIN, 0)
+    if os.environ.get("DSW_CHAIN_DEBUG"):
+        for name, dbg in [("no-claim-ahead", 32), ("no-stores", 8), ("no-Z", 16), ("no-stores-no-Z", 24), ("no-loop", 2), ("no-loop-stores-Z", 26)]:
+            lib.dsw_set_option(OPT_DEBUG, dbg)
+            med, best = timed(lambda: F_.cheb_terms(x, plan, K), flush)
+            print(f"debug {name:18s} median {med:8.1f} us  best {best:8.1f} us", flush=True)
+            if dbg == 32:
+                buf = (ctypes.c_uint64 * 16)()
+                lib.dsw_set_option(OPT_DEBUG, 36)
+                lib.dsw_debug_chain_counters(buf, 1)
+                F_.cheb_terms(x, plan, K)
+                torch.cuda.synchronize()
+                lib.dsw_debug_chain_counters(buf, 1)
+                n, m = max(buf[4], 1), max(buf[15], 1)
+                print("  team: wait-next %.0f  zg+transfer-wait %.0f  loop %.0f  stores %.0f | issuer: metadata %.0f  wait-loop-end %.0f  deps+issue %.0f  late %d of %d" %
+                      (buf[0] / n, buf[1] / n, buf[2] / n, buf[3] / n, buf[8] / m, buf[9] / m, buf[10] / m, buf[14], buf[15]), flush=True)
+        lib.dsw_set_option(OPT_DEBUG, 0)
 
     if os.environ.get("DSW_CHAIN_PHASES"):
-        buf = (ctypes.c_uint64 * 8)()
+        buf = (ctypes.c_uint64 * 16)()
         lib.dsw_set_option(OPT_DEBUG, 4)
         F_.cheb_terms(x, plan, K)
         torch.cuda.synchronize()
@@ -80,8 +96,11 @@ def main():
         torch.cuda.synchronize()
         lib.dsw_debug_chain_counters(buf, 1)
         n = max(buf[4], 1)
-        print("chain phase cycles per item (avg over teams): zg-loads %.0f  wait %.0f  loop %.0f  stores+flag+stage %.0f  items %d" %
+        print("team cycles per item: wait-next %.0f  zg+transfer-wait %.0f  loop %.0f  stores %.0f  items %d" %
               (buf[0] / n, buf[1] / n, buf[2] / n, buf[3] / n, buf[4]), flush=True)
+        m = max(buf[15], 1)
+        print("issuer cycles per item: metadata %.0f  wait-loop-end %.0f  deps+issue %.0f  late %d of %d" %
+              (buf[8] / m, buf[9] / m, buf[10] / m, buf[14], buf[15]), flush=True)
         lib.dsw_set_option(OPT_DEBUG, 0)
 
 
