@@ -20,14 +20,15 @@
 // zeroes the claim counter: no memset launches, and captured CUDA graphs replay correctly.
 //
 // Warp roles (512 threads, registers rebalanced with setmaxnreg):
-//   warps 0-7   four compute teams of two warps.  4 lanes own a row-block of 4 rows x 64 channels (64 fp32
+//   warps 8-15  four compute teams of two warps (the issue arbiter favours high warp ids: the spinning control warps
+//               never take an issue slot a compute warp could use).  4 lanes own a row-block of 4 rows x 64 channels (64 fp32
 //               accumulators per lane); every 16-byte shared-memory read feeds 4 packed FMAs (FFMA2) — the
 //               register-tiled loop of hop_team_kernel (dsw_spmm.cu).  They only ever wait on mbarriers.
-//   warps 8-11  one issuer warp per team, running one item ahead of it: claim, decode, the tile's metadata (one
+//   warps 0-3   one issuer warp per team, running one item ahead of it: claim, decode, the tile's metadata (one
 //               round trip: fixed-stride plan tables), dependency flags (a second one); the moment the team's
 //               entry loop ends it issues the transfers — the tile's weight / offset panels (two bulk copies) and the
 //               distinct source rows the tile gathers (one tensor-map box per run of consecutive rows).
-//   warp 12     publisher: collects the items whose stores have been issued and releases their flags behind ONE
+//   warp 4      publisher: collects the items whose stores have been issued and releases their flags behind ONE
 //               gpu-scope fence per round (a MEMBAR.ALL.GPU costs ~7k cycles on a busy SM: it must not sit on a
 //               compute or issuer warp's path).
 #include <algorithm>
@@ -39,7 +40,6 @@ namespace dsw {
 
 constexpr int CH_TEAMS = 4;
 constexpr int CH_TEAM_THREADS = DSW_TILE_BLOCKS * 4;  // 4 lanes per row-block: two compute warps per team
-constexpr int CH_COMPUTE_THREADS = CH_TEAMS * CH_TEAM_THREADS;
 constexpr int CH_THREADS = 512;                       // 8 compute warps, 4 issuer warps, publisher + 3 idle warps
 constexpr int CH_DESC_RING = 4;                       // item descriptors per team
 constexpr int CH_REGS_COMPUTE = 200, CH_REGS_ISSUER = 64, CH_REGS_PUBLISHER = 40;
@@ -164,8 +164,11 @@ struct TeamWords {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void red_release_cta(uint32_t* p) {
-  asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(p)) : "memory");
+__device__ __forceinline__ void red_release_cta(uint32_t* p, bool relaxed_for_timing_only = false) {
+  if (relaxed_for_timing_only)
+    asm volatile("red.relaxed.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(p)) : "memory");
+  else
+    asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(p)) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_acquire_cta(const uint32_t* p) {
   uint32_t v;
@@ -213,10 +216,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
   int32_t* const claim = P.sync;
   int32_t* const flags = P.sync + DSW_CHAIN_HDR;
 
-  if (warp >= 12) {
+  // Warp roles by warp id: 0-3 issuers, 4 publisher (5-7 idle), 8-15 compute.  The issue arbiter favours high warp
+  // ids, so the spinning control warps never take an issue slot a compute warp could use.
+  if (warp >= 4 && warp < 8) {
     // ========================================= publisher =========================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CH_REGS_PUBLISHER));
-    if (warp == 12) {
+    if (warp == 4) {
       uint32_t pn = 0;  // lane t < CH_TEAMS: items of team t published so far
       bool finished = lane >= CH_TEAMS;
       while (true) {
@@ -245,14 +250,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         } else if (__all_sync(0xffffffffu, finished)) {
           break;
         } else {
-          __nanosleep(40);
+          __nanosleep(400);
         }
       }
     }
-  } else if (warp >= CH_COMPUTE_THREADS / 32) {
+  } else if (warp < 4) {
     // ========================================== issuer ===========================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CH_REGS_ISSUER));
-    const int team = warp - CH_COMPUTE_THREADS / 32;
+    const int team = warp;
     uint8_t* xs = ch_smem + (size_t)team * P.team_stride;
     const uint32_t xs_u32 = smem_u32(xs);
     const uint32_t sval_u32 = xs_u32 + (uint32_t)P.cap_rows * 256u;
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         break;
       }
       int32_t idx_next = 0;
-      const bool claim_ahead = !(P.debug_skip & 32);
+      const bool claim_ahead = (P.debug_skip & 32) != 0;  // measured slower: the deeper claim window makes dependencies late
       if (lane == 0 && claim_ahead) idx_next = atomicAdd(claim, 1);  // consumed at the top of the next round
       // ---- decode item n and fetch its metadata (the team is still busy with item n - 1) ----
       int32_t g, r, Sg;
@@ -362,8 +367,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
   } else {
     // ======================================= compute team =======================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CH_REGS_COMPUTE));
-    const int team = tid / CH_TEAM_THREADS;
-    const int tt = tid - team * CH_TEAM_THREADS;
+    const int ctid = tid - 256;  // compute thread id
+    const int team = ctid / CH_TEAM_THREADS;
+    const int tt = ctid - team * CH_TEAM_THREADS;
     const uint8_t* xs = ch_smem + (size_t)team * P.team_stride;
     const float4* s_val = reinterpret_cast<const float4*>(xs + (size_t)P.cap_rows * 256);
     const uint32_t* s_off =
@@ -392,14 +398,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       const bool early = n > 0 && __shfl_sync(0xffffffffu, (int)mbar_test(bar_ready, n & 1u), 0) != 0;
       if (n > 0 && !early) {
         __syncwarp();
-        if (lane == 0) red_release_cta(done);
+        if (lane == 0) red_release_cta(done, (P.debug_skip & 64) != 0);
       }
       mbar_wait(bar_ready, n & 1u);
       const ItemDesc d = s_item[team * CH_DESC_RING + (n % CH_DESC_RING)];
       if (d.idx < 0) {
         if (early) {
           __syncwarp();
-          if (lane == 0) red_release_cta(done);
+          if (lane == 0) red_release_cta(done, (P.debug_skip & 64) != 0);
         }
         break;
       }
@@ -431,7 +437,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
           }
         if (early && H.G == nullptr) {
           __syncwarp();
-          if (lane == 0) red_release_cta(done);
+          if (lane == 0) red_release_cta(done, (P.debug_skip & 64) != 0);
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r)
@@ -449,7 +455,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
             }
           if (early) {
             __syncwarp();
-            if (lane == 0) red_release_cta(done);
+            if (lane == 0) red_release_cta(done, (P.debug_skip & 64) != 0);
           }
 #pragma unroll
           for (int r = 0; r < 4; ++r)
@@ -553,6 +559,10 @@ static bool chain_ok(const dsw_csr& A, const dsw_rb& rb, const ChainHop* h, int 
   if (g_options[DSW_OPT_HOP_KERNEL].load(std::memory_order_relaxed) != 0) return false;
   if (g_options[DSW_OPT_NO_TMA].load(std::memory_order_relaxed) != 0) return false;
   if (rb.R != 4 || rb.n_tiles <= 0 || rb.perm || !rb.chain_sync || rb.tile_deps_max <= 0) return false;
+  // Measured (tools/bench_layers.py, tools/bench_chain.py): the fused kernel wins where a hop pass has at least one tile per
+  // SM (nside >= 32: 226 vs 260 us at V 12288 / F 64, 802 vs 910 us at nside 64); on the coarse U-Net levels the
+  // per-tile launches, which stage a tile's panels once per CTA, are 5-10 % faster.  DSW_OPT_NO_CHAIN = 2 forces it.
+  if (g_options[DSW_OPT_NO_CHAIN].load(std::memory_order_relaxed) != 2 && rb.n_tiles < sm_count()) return false;
   if (A.n_rows != A.n_cols || F % 4 || B <= 0 || B > 65535) return false;
   const int64_t small_f_opt = g_options[DSW_OPT_HOP_SMALL_F].load(std::memory_order_relaxed);
   if (F <= (small_f_opt > 0 ? (int)small_f_opt : 8)) return false;

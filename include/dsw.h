@@ -260,7 +260,7 @@ enum {
   DSW_OPT_HOP_PREFETCH = 14,  /* the hop kernel L2-prefetches the next item's Z / G rows when it issues its tile transfer (default); 2 = off */
   DSW_OPT_NO_PDL = 15,        /* 1 = launch the hop kernel without programmatic stream serialisation */
   DSW_OPT_PLAN_PERMUTE = 16,  /* locality permutation of the row-block layout at plan creation: 0 = automatic, 1 = never, 2 = always */
-  DSW_OPT_NO_CHAIN = 17,      /* 1 = launch the hops of a recurrence one by one instead of the fused persistent chain kernel */
+  DSW_OPT_NO_CHAIN = 17,      /* 0 = fused persistent chain kernel where it wins (>= one tile per SM), 1 = never (hop-by-hop launches), 2 = wherever it is supported */
   DSW_OPT_CHAIN_L2_BYTES = 18, /* L2 budget (bytes) for the three live planes of a sample group of the chain kernel; 0 = default 64 MiB */
   DSW_OPT_CHAIN_MIN_PASS = 19, /* least number of work items of one hop pass of the chain kernel; 0 = default 2 x teams in flight */
   DSW_OPT_CHAIN_MIN_HOPS = 20, /* chains shorter than this many hops are launched hop by hop; 0 / 1 = every chain is fused */

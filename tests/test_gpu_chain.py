@@ -12,6 +12,7 @@ from _util import REL_TOL, rel_err
 pytestmark = pytest.mark.gpu
 
 OPT_NO_CHAIN, OPT_CHAIN_L2, OPT_CHAIN_MIN_PASS = 17, 18, 19
+HOP_BY_HOP, FUSED = 1, 2   # DSW_OPT_NO_CHAIN: 0 = automatic (fused from one tile per SM on), 1 = never, 2 = wherever supported
 
 
 @pytest.fixture(scope="module")
@@ -51,9 +52,9 @@ def test_chain_is_bit_identical_to_hop_by_hop(nside, B, F, K, group, dev, lib):
     x = torch.randn(B, V, F)
     xg = x.to(dev)
     try:
-        lib.dsw_set_option(OPT_NO_CHAIN, 1)
+        lib.dsw_set_option(OPT_NO_CHAIN, HOP_BY_HOP)
         want = F_.cheb_terms(xg, plan, K)
-        lib.dsw_set_option(OPT_NO_CHAIN, 0)
+        lib.dsw_set_option(OPT_NO_CHAIN, FUSED)
         if group == "one-sample-groups":
             lib.dsw_set_option(OPT_CHAIN_L2, 1)        # budget of one byte: S = 1 unless the pass floor raises it
             lib.dsw_set_option(OPT_CHAIN_MIN_PASS, 1)
@@ -90,7 +91,7 @@ def test_chain_conv_fwd_bwd_bit_identical(fwd_algo, bwd_algo, dev, lib):
     try:
         lib.dsw_set_option(4, fwd_algo)
         lib.dsw_set_option(5, bwd_algo)
-        for no_chain in (1, 0):
+        for no_chain in (HOP_BY_HOP, FUSED):
             lib.dsw_set_option(OPT_NO_CHAIN, no_chain)
             layer.zero_grad()
             xg = x.clone().requires_grad_(True)
@@ -118,9 +119,10 @@ def test_chain_on_nonsymmetric_operator(dev, lib):
     plan = F_.plan_for(A.to(dev))
     B, V, F, K = 4, A.shape[0], 64, 5
     x = torch.randn(B, V, F)
-    got = F_.cheb_terms(x.to(dev), plan, K)
-    lib.dsw_set_option(OPT_NO_CHAIN, 1)
     try:
+        lib.dsw_set_option(OPT_NO_CHAIN, FUSED)
+        got = F_.cheb_terms(x.to(dev), plan, K)
+        lib.dsw_set_option(OPT_NO_CHAIN, HOP_BY_HOP)
         want = F_.cheb_terms(x.to(dev), plan, K)
     finally:
         lib.dsw_set_option(OPT_NO_CHAIN, 0)
@@ -142,9 +144,9 @@ def test_chain_replays_in_a_cuda_graph_and_survives_ring_wrap(dev, lib):
     plan = F_.plan_for(lap)
     B, V, F, K = 5, lap.shape[0], 64, 4
     x = torch.randn(B, V, F, device=dev)
-    lib.dsw_set_option(OPT_NO_CHAIN, 1)
+    lib.dsw_set_option(OPT_NO_CHAIN, HOP_BY_HOP)
     want = F_.cheb_terms(x, plan, K)
-    lib.dsw_set_option(OPT_NO_CHAIN, 0)
+    lib.dsw_set_option(OPT_NO_CHAIN, FUSED)
     for i in range(20):  # > DSW_CHAIN_SETS launches queued back to back
         got = F_.cheb_terms(x, plan, K)
     assert torch.equal(got, want)
@@ -164,10 +166,11 @@ def test_chain_replays_in_a_cuda_graph_and_survives_ring_wrap(dev, lib):
         g.replay()
         torch.cuda.synchronize()
         got = out.clone()
-        lib.dsw_set_option(OPT_NO_CHAIN, 1)
+        lib.dsw_set_option(OPT_NO_CHAIN, HOP_BY_HOP)
         want = F_.cheb_terms(xn, plan, K)
-        lib.dsw_set_option(OPT_NO_CHAIN, 0)
+        lib.dsw_set_option(OPT_NO_CHAIN, FUSED)
         assert torch.equal(got, want), f"replay {rep}"
+    lib.dsw_set_option(OPT_NO_CHAIN, 0)
 
 
 def test_chain_full_size_nside64_matches_hop_by_hop(dev, lib):
@@ -181,8 +184,10 @@ def test_chain_full_size_nside64_matches_hop_by_hop(dev, lib):
     plan = F_.plan_for(lap.to(dev))
     B, V, F, K = 32, lap.shape[0], 64, 4
     x = torch.randn(B, V, F, device=dev)
-    got = F_.cheb_terms(x, plan, K)
-    lib.dsw_set_option(OPT_NO_CHAIN, 1)
+    launches0 = lib.dsw_launch_count()
+    got = F_.cheb_terms(x, plan, K)   # automatic mode: 768 tiles >= one per SM -> one fused launch
+    assert lib.dsw_launch_count() - launches0 == 1
+    lib.dsw_set_option(OPT_NO_CHAIN, HOP_BY_HOP)
     try:
         want = F_.cheb_terms(x, plan, K)
     finally:

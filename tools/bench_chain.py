@@ -70,7 +70,7 @@ def main():
     lib.dsw_set_option(OPT_MIN_PASS, 0)
     lib.dsw_set_option(OPT_NO_CHAIN, 0)
     if os.environ.get("DSW_CHAIN_DEBUG"):
-        for name, dbg in [("no-claim-ahead", 32), ("no-stores", 8), ("no-Z", 16), ("no-stores-no-Z", 24), ("no-loop", 2), ("no-loop-stores-Z", 26)]:
+        for name, dbg in [("claim-ahead", 32), ("relaxed-done(unsafe)", 64), ("relaxed-done+no-Z", 80), ("no-stores", 8), ("no-Z", 16), ("no-stores-no-Z", 24), ("no-loop", 2), ("no-loop-stores-Z", 26)]:
             lib.dsw_set_option(OPT_DEBUG, dbg)
             med, best = timed(lambda: F_.cheb_terms(x, plan, K), flush)
             print(f"debug {name:18s} median {med:8.1f} us  best {best:8.1f} us", flush=True)
