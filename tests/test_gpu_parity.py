@@ -799,3 +799,112 @@ def test_cfg4_unet_nside64_shard_matches_oracle(dev):
     for name, p in net.named_parameters():
         ref = po[name].grad
         assert rel_l2(p.grad, ref) < 2 * REL_TOL, name
+
+
+# ----------------------------------------------------------------------------------------------
+# Parity hardening: teacher-forced pooling indices, full-size cfg3
+# ----------------------------------------------------------------------------------------------
+
+
+class _ForcedNestedMaxPool(torch.nn.Module):
+    """HealpixMaxPool with the argmax taken from a teacher: values gathered at the given fine-node indices."""
+
+    def __init__(self, idx):
+        super().__init__()
+        self.idx = idx  # [B, F, V/4] int64
+
+    def forward(self, x):
+        return torch.gather(x.permute(0, 2, 1), 2, self.idx).permute(0, 2, 1), self.idx
+
+
+class _ForcedMaxValPool(torch.nn.Module):
+    """GeneralMaxValPool with the teacher's (fine row, column) pairs (reference layout: layers.py:1075-1079)."""
+
+    def __init__(self, idx, n_coarse):
+        super().__init__()
+        self.idx, self.n_coarse = idx, n_coarse  # [2, F*B*V'] with the column c = f*B + b major
+
+    def forward(self, x):
+        B, V, F = x.shape
+        flat = x.permute(1, 2, 0).reshape(V, F * B)
+        vals = flat[self.idx[0], self.idx[1]]  # ordered (c, r)
+        return vals.reshape(F, B, self.n_coarse).permute(1, 2, 0), self.idx
+
+
+@pytest.mark.parametrize("name,pool_method,K,seed", [c for c in UNET_CASES if c[1] in ("max", "maxval")])
+def test_unet_max_pools_teacher_forced_indices_hold_1e4_in_tcgen05_mode(name, pool_method, K, seed, dev, lib):
+    """Max-type pooling is discontinuous: one argmax flip (two window entries closer than the arithmetic difference
+    between two implementations) reroutes a value and its gradient, which is why the free-running nets above are only
+    held to aggregate agreement in tcgen05 mode.  Here the pooling decisions are taken from the teacher — the oracle (the
+    reference's arithmetic on the CPU, pinned to the reference's golden vectors) — so that everything else (every
+    convolution on the tensor cores, the unpools, the whole backward) is held to the 1e-4 bar in production arithmetic."""
+    from deepsphere_weather_b200 import models as M
+    from oracle.unet_oracle import build_unet_oracle, fill_parameters
+
+    g = golden(name)
+    laps = [coo_from(g, f"lap{i}") for i in range(3)]
+    args = (M.default_tensor_info(768), "healpix", {"subdivisions": 8, "nest": True})
+    kw = dict(kernel_size_conv=K, pool_method=pool_method, laplacians=laps)
+    x = torch.from_numpy(g["x"])
+
+    teacher = build_unet_oracle(*args, **kw)
+    fill_parameters(teacher, seed)
+    taught = {}
+    hooks = [getattr(teacher, p).register_forward_hook(lambda m, i, o, p=p: taught.__setitem__(p, o[1])) for p in ("pool1", "pool2")]
+    y_ref = teacher(x)
+    (y_ref**2).mean().backward()
+    for h in hooks:
+        h.remove()
+    assert rel_err(y_ref, g["y"]) < REL_TOL  # the teacher itself reproduces the reference
+
+    prev = lib.dsw_get_mix_mode()
+    lib.dsw_set_mix_mode(1)
+    try:
+        model = M.UNetSpherical(*args, **kw)
+        fill_parameters(model, seed)
+        model = model.to(dev)
+        for p, n_coarse in (("pool1", 192), ("pool2", 48)):
+            idx = taught[p].to(dev)
+            setattr(model, p, _ForcedNestedMaxPool(idx) if pool_method == "max" else _ForcedMaxValPool(idx, n_coarse))
+        y = model(x.to(dev))
+        assert rel_err(y, y_ref) < REL_TOL
+        assert rel_err(y, g["y"]) < REL_TOL
+        (y**2).mean().backward()
+        ref_grads = dict(teacher.named_parameters())
+        for n, p in model.named_parameters():
+            assert rel_err(p.grad, ref_grads[n].grad) < 2 * REL_TOL, n
+    finally:
+        lib.dsw_set_mix_mode(prev)
+
+
+def test_cfg3_full_size_unet_loss_and_gradients_match_oracle(dev, lib):
+    """BASELINE.json configs[2] at its full size (nside 32 -> 16 -> 8, B 32, K 4, interp pools): loss and every
+    parameter-gradient norm of one training step against the oracle on the host (production tcgen05 arithmetic)."""
+    from deepsphere_weather_b200 import models as M
+    from oracle.unet_oracle import build_unet_oracle, fill_parameters
+
+    V, B = 12 * 32 * 32, 32
+    args = (M.default_tensor_info(V), "healpix", {"subdivisions": 32, "nest": True})
+    kw = dict(kernel_size_conv=4, pool_method="interp")
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(B, 3, V, 7, generator=gen)
+    y_obs = torch.randn(B, 1, V, 2, generator=gen)
+    model = M.UNetSpherical(*args, **kw)
+    fill_parameters(model, 5)
+    oracle = build_unet_oracle(*args, laplacians=model.laplacians, **kw)
+    oracle.load_state_dict(model.state_dict(), strict=True)
+    crit = torch.nn.MSELoss()
+    loss_ref = crit(oracle(x), y_obs)
+    loss_ref.backward()
+    model = model.to(dev)
+    loss = crit(model(x.to(dev)), y_obs.to(dev))
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) < REL_TOL * abs(loss_ref.item())
+    ref_grads = dict(oracle.named_parameters())
+    tot, tot_ref = 0.0, 0.0
+    for n, p in model.named_parameters():
+        gn, rn = p.grad.norm().item(), ref_grads[n].grad.norm().item()
+        tot, tot_ref = tot + gn**2, tot_ref + rn**2
+        assert abs(gn - rn) <= 1e-3 * max(rn, 1e-9), n
+        assert rel_err(p.grad, ref_grads[n].grad) < 5 * REL_TOL, n
+    assert abs(tot**0.5 - tot_ref**0.5) <= 2 * REL_TOL * tot_ref**0.5
