@@ -151,7 +151,7 @@ struct ItemDesc {
 struct TeamBars {
   uint64_t ready;  // issuer -> team: descriptor written, dependencies met, transfers issued (count 1)
   uint64_t full;   // transfers -> team: rows and panels have landed (count 1 + tx bytes)
-  uint64_t empty;  // team -> issuer: the entry loop is over, the buffers may be overwritten (count 2: one lane per warp)
+  uint64_t empty;  // team -> issuer: the entry loop is over, the buffers may be overwritten (count 64: every lane)
 };
 
 // plain words shared between the roles of one team
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
   if (tid < CH_TEAMS) {
     mbar_init(smem_u32(&s_bars[tid].ready), 1);
     mbar_init(smem_u32(&s_bars[tid].full), 1);
-    mbar_init(smem_u32(&s_bars[tid].empty), CH_TEAM_THREADS / 32);
+    mbar_init(smem_u32(&s_bars[tid].empty), CH_TEAM_THREADS);
     s_words[tid].done[0] = 0, s_words[tid].done[1] = 0, s_words[tid].published = 0, s_words[tid].total = -1;
   }
   if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -494,9 +494,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
           fma_step(acc, w1, x1);
         }
       }
-      // this warp is done with the staged rows and panels
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_empty);
+      // this lane is done with the staged rows and panels (every lane arrives itself: its own shared-memory reads are
+      // then ordered before the issuer's transfers without leaning on a warp-level sync)
+      mbar_arrive(bar_empty);
       if (prof) c3 = clock64();
       // ---- epilogue: O = alpha * acc ----
       if (active && !(P.debug_skip & 8)) {

@@ -33,13 +33,32 @@ inline bool encode_f32_map(CUtensorMap* out, const float* base, int rank, const 
                            const uint32_t* box) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return false;
+  {
+    // cuTensorMapEncodeTiled is a driver call: it needs the device's primary context current on THIS thread.  A thread
+    // that has only used the runtime API lazily (PyTorch's autograd worker on its first backward) has none bound yet.
+    static thread_local int bound_device = -1;
+    int dev = -1;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev != bound_device) {
+      (void)cudaFree(nullptr);
+      bound_device = dev;
+    }
+  }
   cuuint64_t d[5], s[4];
   cuuint32_t b[5], e[5];
   for (int i = 0; i < rank; ++i) d[i] = dims[i], b[i] = box[i], e[i] = 1;
   for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
-  return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), d, s, b, e,
+  CUresult rc = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), d, s, b, e,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc == CUDA_ERROR_INVALID_CONTEXT || rc == CUDA_ERROR_NOT_INITIALIZED) {
+    // A thread that has only used the runtime API lazily (PyTorch's autograd worker on its first backward) has no
+    // driver context bound yet: bind the device's primary context and encode again.
+    (void)cudaFree(nullptr);
+    rc = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), d, s, b, e,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  return rc == CUDA_SUCCESS;
 }
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {

@@ -831,13 +831,20 @@ class _ForcedMaxValPool(torch.nn.Module):
         return vals.reshape(F, B, self.n_coarse).permute(1, 2, 0), self.idx
 
 
-@pytest.mark.parametrize("name,pool_method,K,seed", [c for c in UNET_CASES if c[1] in ("max", "maxval")])
-def test_unet_max_pools_teacher_forced_indices_hold_1e4_in_tcgen05_mode(name, pool_method, K, seed, dev, lib):
-    """Max-type pooling is discontinuous: one argmax flip (two window entries closer than the arithmetic difference
-    between two implementations) reroutes a value and its gradient, which is why the free-running nets above are only
-    held to aggregate agreement in tcgen05 mode.  Here the pooling decisions are taken from the teacher — the oracle (the
-    reference's arithmetic on the CPU, pinned to the reference's golden vectors) — so that everything else (every
-    convolution on the tensor cores, the unpools, the whole backward) is held to the 1e-4 bar in production arithmetic."""
+@pytest.mark.parametrize("name,pool_method,K,seed", UNET_CASES)
+def test_unet_teacher_forced_decisions_hold_1e4_in_tcgen05_mode(name, pool_method, K, seed, dev, lib):
+    """A U-Net has two kinds of discontinuity: the argmax of the max-type pools and the ReLU masks.  One flipped decision
+    (an entry closer to its rival / to zero than the arithmetic difference between two implementations) reroutes a value
+    or switches a gradient path, and the parameter gradients then differ by 1e-3 .. 1e-2 — between this library's exact
+    fp32 and split-bf16 modes just as between the reference's own CPU and CUDA paths.  That is why the free-running nets
+    above are held to the bar element-wise only where no decision sits on the fence.  Here every decision is taken from
+    the teacher — the oracle (the reference's arithmetic on the CPU, pinned to the reference's golden vectors) — so that
+    everything else (every convolution and skip on the tensor cores, the unpools, the whole backward) is held to the
+    1e-4 bar, outputs AND every parameter gradient, in production arithmetic."""
+    from types import SimpleNamespace
+
+    from deepsphere_weather_b200 import functional as F_
+    from deepsphere_weather_b200 import layers as L
     from deepsphere_weather_b200 import models as M
     from oracle.unet_oracle import build_unet_oracle, fill_parameters
 
@@ -849,30 +856,52 @@ def test_unet_max_pools_teacher_forced_indices_hold_1e4_in_tcgen05_mode(name, po
 
     teacher = build_unet_oracle(*args, **kw)
     fill_parameters(teacher, seed)
-    taught = {}
-    hooks = [getattr(teacher, p).register_forward_hook(lambda m, i, o, p=p: taught.__setitem__(p, o[1])) for p in ("pool1", "pool2")]
+    pools, masks, hooks = {}, {}, []
+    for p in ("pool1", "pool2"):
+        hooks.append(getattr(teacher, p).register_forward_hook(lambda m, i, o, p=p: pools.__setitem__(p, o[1])))
+    for n, m in teacher.named_modules():
+        if isinstance(m, M.ConvBlock) and m.act:
+            hooks.append(m.register_forward_hook(lambda m, i, o, n=n: masks.__setitem__(n, (o > 0).float())))
     y_ref = teacher(x)
     (y_ref**2).mean().backward()
     for h in hooks:
         h.remove()
     assert rel_err(y_ref, g["y"]) < REL_TOL  # the teacher itself reproduces the reference
 
+    class PlainConvCheb(L.ConvCheb):  # no fused activation: the mask is applied by the block
+        fused_activations = ()
+
+        def forward(self, inputs):
+            return super().forward(inputs)
+
+    backend = SimpleNamespace(
+        ConvCheb=PlainConvCheb, Linear=L.NodeLinear, rezero_residual=F_.rezero_residual,
+        healpix_pools={"max": (L.HealpixMaxPool, L.HealpixMaxUnpool), "avg": (L.HealpixAvgPool, L.HealpixAvgUnpool)},
+        general_pools=L.PoolUnpoolBlock.getGeneralPoolUnpoolLayer)
     prev = lib.dsw_get_mix_mode()
     lib.dsw_set_mix_mode(1)
     try:
-        model = M.UNetSpherical(*args, **kw)
+        model = M.UNetSpherical(*args, backend=backend, **kw)
         fill_parameters(model, seed)
         model = model.to(dev)
-        for p, n_coarse in (("pool1", 192), ("pool2", 48)):
-            idx = taught[p].to(dev)
-            setattr(model, p, _ForcedNestedMaxPool(idx) if pool_method == "max" else _ForcedMaxValPool(idx, n_coarse))
+        if pool_method != "interp":
+            for p, n_coarse in (("pool1", 192), ("pool2", 48)):
+                idx = pools[p].to(dev)
+                setattr(model, p, _ForcedNestedMaxPool(idx) if pool_method == "max" else _ForcedMaxValPool(idx, n_coarse))
+        n_masked = 0
+        for n, m in model.named_modules():
+            if isinstance(m, M.ConvBlock) and m.act:
+                m.act_fun = lambda t, mask=masks[n].to(dev): t * mask
+                n_masked += 1
+        assert n_masked == len(masks) == 5  # the first block of conv1, conv2, conv3, uconv2, uconv1
         y = model(x.to(dev))
         assert rel_err(y, y_ref) < REL_TOL
         assert rel_err(y, g["y"]) < REL_TOL
         (y**2).mean().backward()
         ref_grads = dict(teacher.named_parameters())
-        for n, p in model.named_parameters():
-            assert rel_err(p.grad, ref_grads[n].grad) < 2 * REL_TOL, n
+        errs = {n: rel_err(p.grad, ref_grads[n].grad) for n, p in model.named_parameters()}
+        worst = max(errs, key=errs.get)
+        assert errs[worst] < REL_TOL, (worst, errs[worst])
     finally:
         lib.dsw_set_mix_mode(prev)
 
