@@ -645,16 +645,8 @@ static int launch_chain_fused(const dsw_csr& A, const dsw_rb& rb, const ChainHop
     for (int q = 0; q < 8; ++q) maps.m[j][q] = maps.m[0][q];
   }
 
-  static std::atomic<int> attr_dev_mask[2] = {{0}, {0}};  // per device ordinal (0..63): attribute applied
-  int dev = 0;
-  DSW_CUDA_TRY(cudaGetDevice(&dev));
-  {
-    std::atomic<int>& m = attr_dev_mask[(dev >> 5) & 1];
-    if (!(m.load(std::memory_order_acquire) & (1 << (dev & 31)))) {
-      DSW_CUDA_TRY(cudaFuncSetAttribute(hop_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      m.fetch_or(1 << (dev & 31), std::memory_order_release);
-    }
-  }
+  static PerDeviceOnce attr_set;
+  DSW_CUDA_TRY(attr_set.max_dynamic_smem(hop_chain_kernel, 227 * 1024));
   DSW_CUDA_TRY(launch_pdl(hop_chain_kernel, dim3(P.n_ctas), dim3(CH_THREADS), smem, st, pdl_enabled(), P, args, maps));
   return check_launch();
 }

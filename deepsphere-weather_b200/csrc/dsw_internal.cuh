@@ -124,6 +124,24 @@ inline int split_mode() {
   return v == 1 ? 0 : v == 2 ? 2 : 1;
 }
 
+// One-time-per-DEVICE guard for cudaFuncSetAttribute (function attributes belong to a device's context: a process-wide
+// "done" flag would leave the > 48 KB shared-memory kernels un-opted-in on a second GPU).  The attribute is applied
+// BEFORE the bit is published, so a second host thread either sees the bit (attribute in place) or applies it again.
+struct PerDeviceOnce {
+  std::atomic<uint64_t> mask{0};
+  template <class Kern>
+  cudaError_t max_dynamic_smem(Kern kern, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) mask.fetch_or(bit, std::memory_order_release);
+    return e;
+  }
+};
+
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -862,14 +862,12 @@ int launch_mix_tc_ws(const MixArgs& a, void* prep, size_t prep_bytes, bool do_pr
     Q.tc.stages = tc::tma_stages_for(P.BN);
     if (tc::encode_a_maps(a, &Q)) {
       const size_t smem = tc::tma_smem_bytes_for(P.BN);
-      static std::atomic<bool> attr_tma[2] = {{false}, {false}};
+      static PerDeviceOnce attr_tma[2];
       if (a.R != nullptr) {
-        if (!attr_tma[1].exchange(true))
-          DSW_CUDA_TRY(cudaFuncSetAttribute(tc::mix_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DSW_CUDA_TRY(attr_tma[1].max_dynamic_smem(tc::mix_tma_kernel<true>, 227 * 1024));
         DSW_CUDA_TRY(launch_pdl(tc::mix_tma_kernel<true>, grid, dim3(tc::THREADS2), smem, st, pdl_enabled(), Q));
       } else {
-        if (!attr_tma[0].exchange(true))
-          DSW_CUDA_TRY(cudaFuncSetAttribute(tc::mix_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        DSW_CUDA_TRY(attr_tma[0].max_dynamic_smem(tc::mix_tma_kernel<false>, 227 * 1024));
         DSW_CUDA_TRY(launch_pdl(tc::mix_tma_kernel<false>, grid, dim3(tc::THREADS2), smem, st, pdl_enabled(), Q));
       }
       return check_launch();
@@ -878,14 +876,12 @@ int launch_mix_tc_ws(const MixArgs& a, void* prep, size_t prep_bytes, bool do_pr
 
   const size_t smem = tc::smem_bytes_for(P.BN);
   P.stages = tc::stages_for(P.BN);
-  static std::atomic<bool> attr_set[2] = {{false}, {false}};
+  static PerDeviceOnce attr_set[2];
   if (vec4) {
-    if (!attr_set[1].exchange(true))
-      DSW_CUDA_TRY(cudaFuncSetAttribute(tc::mix_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DSW_CUDA_TRY(attr_set[1].max_dynamic_smem(tc::mix_tc_kernel<true>, 227 * 1024));
     tc::mix_tc_kernel<true><<<grid, tc::THREADS2, smem, st>>>(P);
   } else {
-    if (!attr_set[0].exchange(true))
-      DSW_CUDA_TRY(cudaFuncSetAttribute(tc::mix_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DSW_CUDA_TRY(attr_set[0].max_dynamic_smem(tc::mix_tc_kernel<false>, 227 * 1024));
     tc::mix_tc_kernel<false><<<grid, tc::THREADS2, smem, st>>>(P);
   }
   return check_launch();

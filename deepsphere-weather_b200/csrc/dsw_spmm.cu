@@ -801,9 +801,8 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
       const bool lpr8 = g_options[DSW_OPT_HOP_LPR].load(std::memory_order_relaxed) == 8;
       P.pdl = g_options[DSW_OPT_NO_PDL].load(std::memory_order_relaxed) == 0 ? 1 : 0;
       auto launch = [&](auto kern, int threads, int slot) -> int {
-        static std::atomic<bool> attr_done[6] = {{false}, {false}, {false}, {false}, {false}, {false}};
-        if (!attr_done[slot].exchange(true))
-          DSW_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        static PerDeviceOnce attr_done[6];
+        DSW_CUDA_TRY(attr_done[slot].max_dynamic_smem(kern, 226 * 1024));
         if (P.pdl) {
           cudaLaunchConfig_t cfg = {};
           cfg.gridDim = grid, cfg.blockDim = dim3(threads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
@@ -838,15 +837,13 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
       int ns = 1;
       while (ns < 8 && ns * 2 <= a.B && (int64_t)n_tiles * slabs * ceil_div(a.B, ns * 2) >= 148 * 6) ns *= 2;
       dim3 grid(n_tiles, slabs, ceil_div(a.B, ns));
-      static std::atomic<bool> attr_set[2] = {{false}, {false}};
+      static PerDeviceOnce attr_set[2];
       if (nf == 2) {
-        if (smem > 48 * 1024 && !attr_set[1].exchange(true))
-          DSW_CUDA_TRY(cudaFuncSetAttribute(hop_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if (smem > 48 * 1024) DSW_CUDA_TRY(attr_set[1].max_dynamic_smem(hop_tile_kernel<2>, 200 * 1024));
         hop_tile_kernel<2><<<grid, TILE_THREADS, smem, st>>>(rb.blkptr, rb.ucol, reinterpret_cast<const float4*>(rb.uval),
                                                              rb.n_blocks, A.n_rows, ns, a);
       } else {
-        if (smem > 48 * 1024 && !attr_set[0].exchange(true))
-          DSW_CUDA_TRY(cudaFuncSetAttribute(hop_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if (smem > 48 * 1024) DSW_CUDA_TRY(attr_set[0].max_dynamic_smem(hop_tile_kernel<1>, 200 * 1024));
         hop_tile_kernel<1><<<grid, TILE_THREADS, smem, st>>>(rb.blkptr, rb.ucol, reinterpret_cast<const float4*>(rb.uval),
                                                              rb.n_blocks, A.n_rows, ns, a);
       }

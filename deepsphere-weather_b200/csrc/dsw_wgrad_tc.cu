@@ -841,12 +841,11 @@ int launch_wgrad_tc(const WgradArgs& a, size_t partial_bytes, cudaStream_t st) {
       // tensor cores, so the per-SM read traffic does not drop, and the cross-CTA barriers add latency — hence
       // opt-in only: DSW_OPT_WGRAD_PAIR = 1)
       const bool pair = (mtiles % 2 == 0) && (P.nb % 2 == 0) && g_options[DSW_OPT_WGRAD_PAIR].load(std::memory_order_relaxed) == 1;
-      static std::atomic<bool> attr_tma[2] = {{false}, {false}};
+      static PerDeviceOnce attr_tma[2];
       if (pair) {
         const int nbl = P.nb / 2;
         Q.stages = wtc::tma_stages_for(nbl);
-        if (!attr_tma[1].exchange(true))
-          DSW_CUDA_TRY(cudaFuncSetAttribute(wtc::wgrad_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        DSW_CUDA_TRY(attr_tma[1].max_dynamic_smem(wtc::wgrad_tma_kernel<true>, 226 * 1024));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid, cfg.blockDim = dim3(wtc::T_THREADS), cfg.dynamicSmemBytes = wtc::tma_smem_bytes_for(nbl), cfg.stream = st;
         cudaLaunchAttribute attr[1];
@@ -856,8 +855,7 @@ int launch_wgrad_tc(const WgradArgs& a, size_t partial_bytes, cudaStream_t st) {
         DSW_CUDA_TRY(cudaLaunchKernelEx(&cfg, wtc::wgrad_tma_kernel<true>, Q));
         return check_launch();
       }
-      if (!attr_tma[0].exchange(true))
-        DSW_CUDA_TRY(cudaFuncSetAttribute(wtc::wgrad_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+      DSW_CUDA_TRY(attr_tma[0].max_dynamic_smem(wtc::wgrad_tma_kernel<false>, 226 * 1024));
       DSW_CUDA_TRY(launch_pdl(wtc::wgrad_tma_kernel<false>, grid, dim3(wtc::T_THREADS), wtc::tma_smem_bytes_for(P.nb), st,
                               pdl_enabled(), Q));
       return check_launch();
@@ -865,10 +863,8 @@ int launch_wgrad_tc(const WgradArgs& a, size_t partial_bytes, cudaStream_t st) {
   }
   if (P.pp > 1) return launch_wgrad_simt(P.w, st);  // the register-path kernel does not span planes (same partial layout)
   const size_t smem = wtc::smem_bytes_for(P.nb);
-  static std::atomic<bool> attr_set{false};
-  if (!attr_set.exchange(true))
-    DSW_CUDA_TRY(cudaFuncSetAttribute(wtc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)wtc::smem_bytes_for(4)));  // + 1 KB static bias_acc <= 227 KB
+  static PerDeviceOnce attr_set;
+  DSW_CUDA_TRY(attr_set.max_dynamic_smem(wtc::wgrad_tc_kernel, (int)wtc::smem_bytes_for(4)));  // + 1 KB static bias_acc <= 227 KB
   wtc::wgrad_tc_kernel<<<grid, wtc::THREADS, smem, st>>>(P);
   return check_launch();
 }

@@ -55,20 +55,34 @@ class FlatGradBucket:
                 raise RuntimeError("a parameter gradient was detached from the flat bucket "
                                    "(use bucket.zero_() instead of zero_grad(set_to_none=True))")
 
-    def allreduce_mean(self, async_op: bool = False):
-        """Sum the bucket over ranks and divide by the world size (mean gradient)."""
+    def allreduce_mean(self, async_op: bool = False, local_batch: Optional[int] = None, global_batch: Optional[int] = None):
+        """Average the per-rank gradients into the global-batch mean gradient.
+
+        With equal shards (the default) every rank's loss is a mean over the same number of samples and the mean of the
+        per-rank gradients IS the global mean: sum, then divide by the world size.  ``shard_batch`` makes uneven shards
+        when the global batch does not divide; pass ``local_batch`` / ``global_batch`` then and each rank's gradient is
+        weighted by its share of the samples before the sum (a mean of per-shard means would over-weight the samples of
+        the smaller shards)."""
+        if (local_batch is None) != (global_batch is None):
+            raise ValueError("pass both local_batch and global_batch, or neither")
         if self.world_size == 1:
             return None
+        self._post_scale = 1.0 / self.world_size
+        if local_batch is not None:
+            self.flat.mul_(float(local_batch) / float(global_batch))
+            self._post_scale = 1.0
         work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
         if async_op:
             return work
-        self.flat.div_(self.world_size)
+        if self._post_scale != 1.0:
+            self.flat.mul_(self._post_scale)
         return None
 
     def finish(self, work):
         if work is not None:
             work.wait()
-            self.flat.div_(self.world_size)
+            if getattr(self, "_post_scale", 1.0 / self.world_size) != 1.0:
+                self.flat.mul_(getattr(self, "_post_scale", 1.0 / self.world_size))
 
 
 def shard_batch(global_batch: int, rank: int, world_size: int):

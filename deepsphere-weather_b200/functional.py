@@ -51,6 +51,15 @@ def set_save_terms(flag: bool) -> None:
     _SAVE_TERMS = bool(flag)
 
 
+def _require_same_device(ref: torch.Tensor, **others):
+    """The kernels take raw pointers: tensors of different devices would be a peer access fault or a silent cross-device
+    read where the reference raises a device-mismatch error."""
+    for name, t in others.items():
+        dev = getattr(t, "device", None)
+        if t is not None and dev is not None and dev != ref.device:
+            raise RuntimeError(f"{name} is on {dev} but the inputs are on {ref.device}: all operands must share one CUDA device")
+
+
 def _workspace(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
 
@@ -94,29 +103,42 @@ class SparsePlan:
         return int(_lib.load().dsw_plan_operand_bytes(self.handle))
 
 
-_PLAN_CACHE: dict = {}
+_PLAN_CACHE: dict = {}        # content digest -> SparsePlan (strong; bounded, least recently used first out)
+_PLAN_BY_TENSOR: dict = {}    # id(tensor) -> (weakref to the tensor, its _version, plan); dropped when the tensor dies
+_PLAN_CACHE_MAX = 64
+
+
+def _operator_digest(c: torch.Tensor) -> tuple:
+    """Content key of a coalesced sparse COO operator: a 128-bit digest of the exact (indices, values) bytes.  (A
+    checksum of sums is not enough: all permutation matrices of one size, or two one-hot pooling matrices whose winner
+    indices add up alike, would share it and silently reuse each other's plan.)"""
+    import hashlib
+
+    h = hashlib.blake2b(digest_size=16)
+    h.update(c.indices().cpu().contiguous().numpy().tobytes())
+    h.update(c.values().to(torch.float32).cpu().contiguous().numpy().tobytes())
+    return (c.device.index, tuple(c.shape), int(c.values().numel()), h.hexdigest())
 
 
 def plan_for(coo: torch.Tensor) -> SparsePlan:
-    """Plan cache keyed by operator content (modules of one U-Net level share a Laplacian but
-    ``module.to(device)`` gives each its own copy of the buffer)."""
+    """Plan cache keyed by operator content (modules of one U-Net level share a Laplacian but ``module.to(device)`` gives
+    each its own copy of the buffer).  The digest costs one device-to-host copy per *new* buffer object; afterwards the
+    buffer is recognised by identity and version."""
     if not coo.is_cuda:
         raise RuntimeError("sparse operator must live on a CUDA device (no CPU path)")
-    ident = (coo.device.index, id(coo), coo._version if hasattr(coo, "_version") else 0)
-    hit = _PLAN_CACHE.get(ident)
-    if hit is not None and hit[0]() is coo:
-        return hit[1]
+    ident = id(coo)
+    hit = _PLAN_BY_TENSOR.get(ident)
+    if hit is not None and hit[0]() is coo and hit[1] == coo._version:
+        return hit[2]
     c = coo.coalesce()
-    vals, idx = c.values(), c.indices()
-    key = (
-        coo.device.index, tuple(coo.shape), int(vals.numel()),
-        float(vals.double().sum()), float((vals.double() * (idx[0] + 2 * idx[1] + 1)).sum()),
-    )
-    plan = _PLAN_CACHE.get(key)
+    key = _operator_digest(c)
+    plan = _PLAN_CACHE.pop(key, None)
     if plan is None:
         plan = SparsePlan(c)
-        _PLAN_CACHE[key] = plan
-    _PLAN_CACHE[ident] = (weakref.ref(coo), plan)
+    _PLAN_CACHE[key] = plan  # (re-)inserted last: most recently used
+    while len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
+        _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+    _PLAN_BY_TENSOR[ident] = (weakref.ref(coo, lambda _r, ident=ident: _PLAN_BY_TENSOR.pop(ident, None)), coo._version, plan)
     return plan
 
 
@@ -140,6 +162,7 @@ class ChebConvFunction(torch.autograd.Function):
             )
         if V != plan.shape[0]:
             raise ValueError(f"inputs have {V} nodes but the laplacian is {plan.shape}")
+        _require_same_device(x, weight=weight, bias=bias, laplacian=plan)
         lib = _lib.load()
         x = _channel_last(x)
         w = weight.contiguous()
@@ -211,6 +234,7 @@ def cheb_conv(x, weight, bias, plan: SparsePlan, act: int = 0):
 def cheb_terms(x: torch.Tensor, plan: SparsePlan, K: int) -> torch.Tensor:
     """The recurrence alone: ``[K-1, B, V, F]`` holding T_1 x .. T_{K-1} x (layers.py:163-169)."""
     _require_cuda_f32(x, "inputs")
+    _require_same_device(x, laplacian=plan)
     x = _channel_last(x)
     B, V, F = x.shape
     out = torch.empty((max(K - 1, 0), B, V, F), dtype=torch.float32, device=x.device)
@@ -409,6 +433,7 @@ class RemapFunction(torch.autograd.Function):
         B, V, F = x.shape
         if V != plan.shape[1]:
             raise ValueError(f"x has {V} nodes but remap_matrix is {plan.shape}")
+        _require_same_device(x, remap_matrix=plan)
         x = _channel_last(x)
         y = torch.empty((B, plan.shape[0], F), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
@@ -449,6 +474,7 @@ class MaxValPoolFunction(torch.autograd.Function):
         _require_cuda_f32(x, "x")
         B, V, F = x.shape
         assert V == plan.shape[1], "remap_matrix.shape[1] != x.shape[1]"  # layers.py:1048
+        _require_same_device(x, remap_matrix=plan)
         Vc = plan.shape[0]
         x = _channel_last(x)
         y = torch.empty((B, Vc, F), dtype=torch.float32, device=x.device)

@@ -119,19 +119,37 @@ def knn_laplacian(xyz: np.ndarray, k: int = 20) -> sparse.csr_matrix:
 
 
 def estimate_lmax_deterministic(L: sparse.spmatrix, iters: int = 64) -> float:
-    """Largest eigenvalue by power iteration from a fixed start vector, with the reference's 1 %
-    safety margin (``estimate_lmax`` at ``layers.py:57-69`` uses ARPACK with a *random* start, so
-    two reference calls differ by ~1e-3).  Deterministic by construction."""
+    """Largest eigenvalue of ``L`` with the reference's 1 % safety margin (``estimate_lmax``, ``layers.py:57-69``),
+    deterministically.  The reference asks ARPACK with a *random* start vector, so two of its calls differ by ~1e-3
+    (SURVEY.md §0.4); here ARPACK gets a fixed start vector and a tight tolerance, which makes the estimate reproducible
+    AND converged — an unconverged power iteration approaches lmax from below and would leave the rescaled operator
+    ``2 L / lmax - I`` with eigenvalues above 1, outside the interval the Chebyshev recurrence assumes.  Like the
+    reference the result is capped at 2 (the bound for normalised Laplacians is exact there, ``layers.py:66-68``)."""
+    from scipy.sparse import linalg as sla
+
     n = L.shape[0]
-    v = np.cos(np.arange(n, dtype=np.float64) * 0.7390851332151607) + 1.5
-    v /= np.linalg.norm(v)
-    lam = 0.0
-    for _ in range(iters):
-        w = L @ v
-        lam = float(np.linalg.norm(w))
-        if lam == 0.0:
-            break
-        v = w / lam
+    v0 = np.cos(np.arange(n, dtype=np.float64) * 0.7390851332151607) + 1.5
+    Ld = sparse.csr_matrix(L, dtype=np.float64)
+    lam = None
+    if n > 3:
+        try:
+            lam = float(sla.eigsh(Ld, k=1, which="LA", v0=v0, tol=1e-9, maxiter=max(10 * n, 1000), return_eigenvectors=False)[0])
+        except sla.ArpackError:
+            lam = None
+    if lam is None:  # tiny operators / no convergence: power iteration until the Rayleigh quotient settles
+        v = v0 / np.linalg.norm(v0)
+        lam = 0.0
+        for _ in range(max(iters, 1) * 64):
+            w = Ld @ v
+            nw = float(np.linalg.norm(w))
+            if nw == 0.0:
+                break
+            new = float(v @ w)
+            v = w / nw
+            if abs(new - lam) <= 1e-10 * max(abs(new), 1.0):
+                lam = new
+                break
+            lam = new
     return lam * (1.0 + 2.0 * 5e-3)
 
 

@@ -10,7 +10,7 @@ import torch
 from torch.autograd.function import once_differentiable
 
 from . import _lib
-from .functional import _require_cuda_f32, _stream_ptr, _workspace
+from .functional import _require_cuda_f32, _require_same_device, _stream_ptr, _workspace
 
 
 class _WeightedMSEFunction(torch.autograd.Function):
@@ -18,6 +18,7 @@ class _WeightedMSEFunction(torch.autograd.Function):
     def forward(ctx, pred, label, weights, reduction: str):
         _require_cuda_f32(pred, "pred")
         _require_cuda_f32(label, "label")
+        _require_same_device(pred, label=label, weights=weights)
         lib = _lib.load()
         p, l = pred.contiguous(), label.contiguous()
         B, V, F = p.shape
@@ -46,8 +47,10 @@ class _WeightedMSEFunction(torch.autograd.Function):
         B, V, F = ctx.dims
         saved = ctx.saved_tensors
         g = g.contiguous()
-        if not ctx.needs_input_grad[0]:
+        if not (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
             return None, None, None, None
+        # d/d label of w (pred - label)^2 is minus d/d pred: the reference's MSE propagates it when the label needs it
+        both = lambda grad: (grad if ctx.needs_input_grad[0] else None, -grad if ctx.needs_input_grad[1] else None, None, None)
         if ctx.reduction == "none":
             p, l, *w = saved
             grad = torch.empty_like(p)
@@ -55,14 +58,14 @@ class _WeightedMSEFunction(torch.autograd.Function):
                 rc = lib.dsw_wmse_none_bwd(p.data_ptr(), l.data_ptr(), w[0].data_ptr() if w else None, g.data_ptr(), grad.data_ptr(),
                                            B, V, F, _stream_ptr(p.device))
             _lib.check(rc, "dsw_wmse_none_bwd")
-            return grad, None, None, None
+            return both(grad)
         p, l, ws, *w = saved
         grad = torch.empty_like(p)
         with torch.cuda.device(p.device):
             rc = lib.dsw_wmse_bwd(p.data_ptr(), l.data_ptr(), w[0].data_ptr() if w else None, ws.data_ptr(), g.data_ptr(),
                                   grad.data_ptr(), B, V, F, _stream_ptr(p.device))
         _lib.check(rc, "dsw_wmse_bwd")
-        return grad, None, None, None
+        return both(grad)
 
 
 class WeightedMSELoss(torch.nn.MSELoss):

@@ -18,7 +18,10 @@
  *  - node features are fp32, channel-last: x[b][v][f] at x + b*sB + v*sV + f (element strides,
  *    feature stride 1).  Outputs are written densely ([B][V][F] contiguous);
  *  - return value: 0 on success, a negative dsw_status otherwise; dsw_strerror() names it.
- *  - re-entrant: no global mutable state; plans are immutable after creation.
+ *  - re-entrant: calls may come from any host thread (PyTorch runs the backward on its autograd worker).  The only
+ *    process-wide mutable state are the tuning switches (dsw_set_option / dsw_set_mix_mode: relaxed atomics read at
+ *    launch time) and the launch counter; a plan's device arrays are immutable after creation except its scheduling
+ *    words (claim counters, chain-kernel flags), which every launch leaves zeroed / advanced for the next one.
  */
 #ifndef DSW_H_
 #define DSW_H_
@@ -78,8 +81,8 @@ int64_t dsw_plan_operand_bytes(const dsw_plan* plan);
  * ConvCheb.forward (layers.py:365-376):
  *     y[b,v,:] = bias + sum_{k<K} (T_k(L) x_b)[v,:] . W[:,k,:],   T_0=I, T_1=L, T_k=2 L T_{k-1}-T_{k-2}
  * W is the reference's parameter layout [Fin][K][Fout] contiguous; bias [Fout] or NULL.
- * act: 0 = none, 1 = ReLU applied after the bias (ConvBlock.forward, my_models_graph.py:104-118; only
- * with the TERMS order, DSW_ERR_UNSUPPORTED otherwise).
+ * act: 0 = none, 1 = ReLU applied after the bias (ConvBlock.forward, my_models_graph.py:104-118): in the epilogue of the
+ * channel mix (TERMS order) or of the last hop (CLENSHAW order).
  * Workspace holds the intermediate planes (K-1 Chebyshev terms of x, or K planes x.W_k).
  * ------------------------------------------------------------------------------------------- */
 size_t dsw_cheb_fwd_workspace_bytes(int32_t B, int32_t V, int32_t Fin, int32_t Fout, int32_t K);

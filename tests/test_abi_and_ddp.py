@@ -150,3 +150,63 @@ def test_flat_bucket_allreduce_equals_single_process_gradient_gloo_ws2():
     loss.backward()
     full = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
     assert torch.allclose(ret["flat"], full, rtol=1e-5, atol=1e-6)
+
+
+def _ddp_uneven_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(100 + rank)
+        net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+        bucket = FlatGradBucket(net)
+        g = torch.Generator().manual_seed(7)
+        total = 7  # 4 + 3 samples: uneven shards
+        x, y = torch.randn(total, 6, generator=g), torch.randn(total, 3, generator=g)
+        s0, s1 = shard_batch(total, rank, world)
+        bucket.zero_()
+        loss = ((net(x[s0:s1]) - y[s0:s1]) ** 2).mean()   # a per-shard MEAN, as the training loop computes it
+        loss.backward()
+        bucket.allreduce_mean(local_batch=s1 - s0, global_batch=total)
+        if rank == 0:
+            ret["flat"] = bucket.flat.clone()
+            ret["params"] = [p.detach().clone() for p in net.parameters()]
+            ret["x"], ret["y"] = x, y
+    finally:
+        dist.destroy_process_group()
+
+
+def test_uneven_shards_are_weighted_by_their_share_of_the_batch_gloo_ws2():
+    """a mean of per-shard means over-weights the smaller shard; weighted by local / global batch the
+    all-reduced gradient equals the single-process global-batch mean gradient."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_ddp_uneven_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3))
+    with torch.no_grad():
+        for p, q in zip(net.parameters(), ret["params"]):
+            p.copy_(q)
+    loss = ((net(ret["x"]) - ret["y"]) ** 2).mean()
+    loss.backward()
+    full = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+    assert torch.allclose(ret["flat"], full, rtol=1e-5, atol=1e-6)
+
+
+def test_lmax_estimate_is_converged_and_deterministic():
+    """the estimate must not undershoot (the rescaled Laplacian has to stay inside [-1, 1])."""
+    import numpy as np
+    from scipy.sparse import linalg as sla
+
+    from deepsphere_weather_b200 import graphs as G
+
+    for nside in (4, 16):
+        L = G.knn_laplacian(G.healpix_nested_xyz(nside), 20)
+        a, b = G.estimate_lmax_deterministic(L), G.estimate_lmax_deterministic(L)
+        assert a == b
+        true = float(sla.eigsh(L.astype(np.float64), k=1, which="LA", return_eigenvectors=False, tol=1e-10)[0])
+        assert true <= a <= true * 1.011, (nside, a, true)
+        Ls = G.prepare_torch_laplacian(L).to_dense().double().numpy()
+        ev = np.linalg.eigvalsh(Ls) if nside == 4 else None
+        if ev is not None:
+            assert ev.max() <= 1.0 + 1e-6 and ev.min() >= -1.0 - 1e-6

@@ -937,3 +937,38 @@ def test_cfg3_full_size_unet_loss_and_gradients_match_oracle(dev, lib):
         assert abs(gn - rn) <= 1e-3 * max(rn, 1e-9), n
         assert rel_err(p.grad, ref_grads[n].grad) < 5 * REL_TOL, n
     assert abs(tot**0.5 - tot_ref**0.5) <= 2 * REL_TOL * tot_ref**0.5
+
+
+def test_plan_cache_tells_permutation_matrices_apart(dev):
+    """two different operators with equal shape, nnz and value / index sums (all permutation matrices of one
+    size) must not share a plan."""
+    from deepsphere_weather_b200 import functional as F_
+
+    n = 64
+    torch.manual_seed(0)
+    pa, pb = torch.randperm(n), torch.randperm(n)
+    rows = torch.arange(n)
+    A = torch.sparse_coo_tensor(torch.stack([rows, pa]), torch.ones(n), (n, n)).coalesce().to(dev)
+    Bm = torch.sparse_coo_tensor(torch.stack([rows, pb]), torch.ones(n), (n, n)).coalesce().to(dev)
+    x = torch.randn(2, n, 8, device=dev)
+    ya = F_.remap(x, F_.plan_for(A))
+    yb = F_.remap(x, F_.plan_for(Bm))
+    assert torch.equal(ya, x[:, pa.to(dev)])
+    assert torch.equal(yb, x[:, pb.to(dev)])
+    assert F_.plan_for(A) is F_.plan_for(A.clone())  # same content, new buffer object: one plan
+
+
+def test_weighted_mse_label_gradient_and_device_checks(dev):
+    from deepsphere_weather_b200 import functional as F_
+    from deepsphere_weather_b200 import graphs as G
+    from deepsphere_weather_b200.losses import WeightedMSELoss
+
+    torch.manual_seed(2)
+    p = torch.randn(2, 48, 3, device=dev, requires_grad=True)
+    l = torch.randn(2, 48, 3, device=dev, requires_grad=True)
+    w = torch.rand(48, device=dev) + 0.5
+    loss = WeightedMSELoss(weights=w)(p, l)
+    loss.backward()
+    assert torch.equal(l.grad, -p.grad) and float(p.grad.abs().max()) > 0
+    with pytest.raises(RuntimeError, match="CUDA|device"):
+        F_.cheb_terms(torch.randn(1, 48, 4), F_.plan_for(G.healpix_laplacian(2).to(dev)), 3)
