@@ -280,6 +280,43 @@ static std::vector<int32_t> locality_order(const HostCsr& a, int32_t cluster_row
   return order;
 }
 
+// Row-major 2-D grids (equiangular lat x lon sampling in lat-major order, cfg5): 64 consecutive nodes are a strip along
+// one latitude row, so a tile gathers its strip plus the strips of the rows above and below (~280 source rows where a
+// compact patch needs ~150).  The grid width W shows in the operator itself: the column offsets +-1 (same row) and +-W
+// (the rows above / below) occur in most rows.  Returns W, or 0 when the operator does not look like such a grid.
+static int32_t detect_row_major_width(const HostCsr& a) {
+  const int32_t n = a.n_rows;
+  if (n != a.n_cols || n < 256) return 0;
+  const int32_t limit = std::min<int32_t>(n / 4, 1 << 16);
+  std::vector<int32_t> cnt(static_cast<size_t>(limit) + 1, 0);
+  for (int32_t r = 0; r < n; ++r)
+    for (int32_t e = a.rowptr[r]; e < a.rowptr[r + 1]; ++e) {
+      const int32_t d = a.col[e] - r;
+      if (d > 0 && d <= limit) cnt[d]++;
+    }
+  if (cnt[1] < n / 2) return 0;
+  for (int32_t w = 8; w <= limit; ++w)
+    if (cnt[w] >= n / 2 && n % w == 0) return w;
+  return 0;
+}
+
+// Patch order of a row-major H x W grid: tiles of th x tw nodes (one tile of the hop kernel), inside a tile 2 x 2 blocks
+// (one row-block of four nodes with a small column union), inside a block row-major.
+static std::vector<int32_t> grid_patch_order(int32_t H, int32_t W, int32_t th, int32_t tw) {
+  std::vector<int32_t> order;
+  order.reserve(static_cast<size_t>(H) * W);
+  for (int32_t ty = 0; ty < H; ty += th)
+    for (int32_t tx = 0; tx < W; tx += tw)
+      for (int32_t by = 0; by < th; by += 2)
+        for (int32_t bx = 0; bx < tw; bx += 2)
+          for (int32_t dy = 0; dy < 2; ++dy)
+            for (int32_t dx = 0; dx < 2; ++dx) {
+              const int32_t y = ty + by + dy, x = tx + bx + dx;
+              if (y < H && x < W) order.push_back(y * W + x);
+            }
+  return order;
+}
+
 static double avg_tile_rows(const HostRb& rb) {
   return rb.n_tiles > 0 ? static_cast<double>(rb.tile_row.size()) / rb.n_tiles : 0.0;
 }
@@ -291,6 +328,16 @@ static HostRb build_rb_auto(const HostCsr& a, int32_t R) {
   const int64_t opt = g_options[DSW_OPT_PLAN_PERMUTE].load(std::memory_order_relaxed);  // 0 auto, 1 never, 2 always
   if (R != 4 || a.n_rows != a.n_cols || nat.n_tiles < 4 || opt == 1) return nat;
   const double rows_per_tile = 4.0 * DSW_TILE_BLOCKS;
+  // Row-major lat-lon grids: tile 4 x 16 patches instead of 1 x 64 strips (cfg5: 281 -> 151 gathered rows per tile, as
+  // many as a HEALPix nested tile; 16 instead of 10 TMA boxes).  Tried whenever the natural order gathers >= 3x its rows.
+  if (opt != 2 && avg_tile_rows(nat) >= 3.0 * rows_per_tile) {
+    const int32_t W = detect_row_major_width(a);
+    if (W > 0) {
+      const std::vector<int32_t> order = grid_patch_order(a.n_rows / W, W, 4, 16);
+      HostRb grid = build_rb(a, R, &order);
+      if (grid.n_tiles > 0 && avg_tile_rows(grid) < 0.75 * avg_tile_rows(nat)) return grid;
+    }
+  }
   // Automatic mode permutes only when the natural order is hopeless (a tile would gather > 6x its own rows, e.g.
   // randomly numbered nodes: the tile kernel would not even fit two teams).  A row-major lat-lon grid (4.4x,
   // cfg5) measured 8 % *slower* permuted: the region-grown patches need 3-4x more, smaller TMA boxes.
