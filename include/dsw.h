@@ -269,6 +269,30 @@ enum {
   DSW_OPT_CHAIN_MIN_HOPS = 20, /* chains shorter than this many hops are launched hop by hop; 0 / 1 = every chain is fused */
   DSW_OPT_COUNT = 21
 };
+/* ---------------------------------------------------------------------------------------------
+ * Device-side construction of the operators that feed the path.
+ *
+ * dsw_graph_knn_laplacian: symmetrised Gaussian k-NN graph of V unit vectors xyz[V][3] (fp64, device) and its normalised
+ * Laplacian L = I - D^-1/2 W D^-1/2 — what the reference obtains from pygsp (modules/models.py:43-46:
+ * SphereHealpix(..., k, lap_type="normalized").L): weights exp(-d^2 / (2 sigma^2)), sigma = mean neighbour distance,
+ * W = max(W, W^T).  rescale = 1 additionally applies prepare_torch_laplacian (modules/layers.py:82-106): 2 L / lmax - I
+ * with lmax = lmax_in if > 0, else a converged, deterministic power iteration x 1.01 (the reference's ARPACK estimate
+ * starts from a random vector).  Output: coalesced COO (row-major, ascending columns) into caller-owned device arrays of
+ * capacity `cap` >= dsw_graph_nnz_capacity(V, k); *nnz_out / *lmax_out are HOST words (the call synchronises the stream:
+ * one-time model construction).  Neighbour ties are broken by the lower node index.
+ *
+ * dsw_graph_nested_pool: the exact pool ([1/kernel] x kernel per coarse row) / unpool ([1] per fine row) pair of nested
+ * orderings (tutorials/interpolation_pooling.ipynb cell 16; the reference computes them with CDO, layers.py:531-581);
+ * n_fine entries each.
+ * ------------------------------------------------------------------------------------------- */
+size_t dsw_graph_workspace_bytes(int32_t V, int32_t k);
+int64_t dsw_graph_nnz_capacity(int32_t V, int32_t k);
+int dsw_graph_knn_laplacian(const double* xyz, int32_t V, int32_t k, int32_t rescale, double lmax_in, int64_t cap, int64_t* coo_row,
+                            int64_t* coo_col, float* coo_val, int64_t* nnz_out, double* lmax_out, void* workspace, size_t workspace_bytes,
+                            void* stream);
+int dsw_graph_nested_pool(int32_t n_fine, int32_t kernel, int64_t* pool_row, int64_t* pool_col, float* pool_val, int64_t* unpool_row,
+                          int64_t* unpool_col, float* unpool_val, void* stream);
+
 /* Tuning only: with DSW_OPT_DEBUG = 4 the hop kernel sums per-phase SM cycles over its teams
  * (issue staging, wait for tile + Z/G, entry loop, stores, item count). */
 int dsw_debug_counters(uint64_t* out8, int reset);

@@ -1,0 +1,102 @@
+"""GPU tests of the device-side operator construction (csrc/dsw_graph.cu) against a host
+restatement of what the reference obtains from pygsp + prepare_torch_laplacian (modules/models.py:43-46,
+modules/layers.py:57-106): symmetrised Gaussian k-NN graph, normalised Laplacian, lmax, rescaling.
+
+Indices must match BIT FOR BIT (same neighbour sets, ties broken by the lower index on both sides); values within 1e-6
+relative (fp64 exp / summation order differ in the last bits before the fp32 cast)."""
+import numpy as np
+import pytest
+import torch
+from scipy import sparse
+from scipy.sparse import linalg as sla
+
+from _util import REL_TOL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev(lib):
+    if not torch.cuda.is_available():
+        pytest.fail("CUDA device required for -m gpu tests (there is no CPU fallback)")
+    return torch.device("cuda:0")
+
+
+def _host_knn_laplacian(xyz: np.ndarray, k: int) -> sparse.csr_matrix:
+    """graphs.knn_laplacian with an explicit tie rule: neighbours ordered by (squared chord length, node index)."""
+    n = xyz.shape[0]
+    nbr = np.empty((n, k), dtype=np.int64)
+    d2 = np.empty((n, k), dtype=np.float64)
+    for a in range(0, n, 512):
+        diff = xyz[a:a + 512, None, :] - xyz[None, :, :]
+        dd = (diff[..., 0] * diff[..., 0] + diff[..., 1] * diff[..., 1]) + diff[..., 2] * diff[..., 2]
+        dd[np.arange(dd.shape[0]), np.arange(a, a + dd.shape[0])] = np.inf
+        order = np.lexsort((np.broadcast_to(np.arange(n), dd.shape), dd), axis=1)[:, :k]
+        nbr[a:a + 512] = order
+        d2[a:a + 512] = np.take_along_axis(dd, order, axis=1)
+    dist = np.sqrt(d2)
+    sigma = dist.mean()
+    w = np.exp(-d2 / (2.0 * sigma**2))
+    W = sparse.csr_matrix((w.ravel(), (np.repeat(np.arange(n), k), nbr.ravel())), shape=(n, n))
+    W = W.maximum(W.T).tocsr()
+    dinv = 1.0 / np.sqrt(np.asarray(W.sum(axis=1)).ravel())
+    L = (sparse.identity(n, format="csr") - sparse.diags(dinv) @ W @ sparse.diags(dinv)).tocsr()
+    L.sort_indices()
+    return L
+
+
+@pytest.mark.parametrize("nside,k", [(4, 20), (8, 20), (16, 20), (8, 8)])
+def test_device_knn_laplacian_matches_host_restatement(nside, k, dev):
+    from deepsphere_weather_b200 import graphs as G
+    from deepsphere_weather_b200 import graphs_device as GD
+
+    xyz = G.healpix_nested_xyz(nside)
+    L = _host_knn_laplacian(xyz, k)
+    # unscaled Laplacian
+    lap, _ = GD.knn_laplacian_device(xyz, k, dev, rescale=False)
+    lap = lap.coalesce()
+    ref = sparse.coo_matrix(L)
+    order = np.lexsort((ref.col, ref.row))
+    assert lap.indices().shape[1] == ref.nnz
+    assert np.array_equal(lap.indices()[0].cpu().numpy(), ref.row[order].astype(np.int64))
+    assert np.array_equal(lap.indices()[1].cpu().numpy(), ref.col[order].astype(np.int64))
+    assert rel_err(lap.values(), ref.data[order].astype(np.float32)) < 1e-6
+    # rescaled: lmax from the device power iteration vs ARPACK on the host operator
+    lap_s, lmax = GD.knn_laplacian_device(xyz, k, dev, rescale=True)
+    true = float(sla.eigsh(L, k=1, which="LA", return_eigenvectors=False, tol=1e-12)[0])
+    assert true * (1.01 - 1e-6) <= lmax <= true * (1.01 + 1e-6), (lmax, true)
+    want = G.prepare_torch_laplacian(L, lmax=lmax).coalesce()
+    got = lap_s.coalesce()
+    assert torch.equal(got.indices().cpu(), want.indices())
+    assert rel_err(got.values(), want.values()) < 1e-6
+    # reproducible: two builds are bit-identical
+    again, lmax2 = GD.knn_laplacian_device(xyz, k, dev, rescale=True)
+    assert lmax2 == lmax and torch.equal(again.coalesce().values(), got.values())
+
+
+def test_device_built_operators_drive_the_convolution(dev):
+    """A ConvCheb on the device-built Laplacian + the device-built nested pool matrices equals the same layers on the
+    host-built operators (graphs.healpix_laplacian uses cKDTree: same graph wherever no neighbour tie sits on the k-th place)."""
+    from deepsphere_weather_b200 import functional as F_
+    from deepsphere_weather_b200 import graphs as G
+    from deepsphere_weather_b200 import graphs_device as GD
+    from deepsphere_weather_b200 import layers as L
+
+    nside = 8
+    V = 12 * nside * nside
+    lap_d = GD.healpix_laplacian_device(nside, 20, dev)
+    xyz = G.healpix_nested_xyz(nside)
+    lap_h = G.prepare_torch_laplacian(_host_knn_laplacian(xyz, 20))
+    torch.manual_seed(0)
+    x = torch.randn(3, V, 16, device=dev)
+    conv_d = L.ConvCheb(16, 24, 4, lap_d).to(dev)
+    conv_h = L.ConvCheb(16, 24, 4, lap_h).to(dev)
+    conv_h.load_state_dict({k: v for k, v in conv_d.state_dict().items() if k != "laplacian"}, strict=False)
+    assert rel_err(conv_d(x), conv_h(x)) < REL_TOL
+    pool_d, unpool_d = GD.nested_pool_matrices_device(V, 4, dev)
+    pool_h, unpool_h = G.nested_pool_matrices(V, 4)
+    for got, want in ((pool_d, pool_h), (unpool_d, unpool_h)):
+        want = G.scipy_to_torch_coo(want)
+        assert torch.equal(got.coalesce().indices().cpu(), want.indices()) and torch.equal(got.coalesce().values().cpu(), want.values())
+    y = F_.remap(x, F_.plan_for(pool_d))
+    assert torch.allclose(y, x.reshape(3, V // 4, 4, 16).mean(2), atol=1e-6)
