@@ -10,6 +10,9 @@
 // node index so that the graph is reproducible (cKDTree's tie order is not).  Output: coalesced COO (row-major, ascending
 // columns), int64 indices + fp32 values — the boundary type of the reference's module buffers (layers.py:584-594).
 #include <algorithm>
+#include <cmath>
+
+#include <cub/device/device_radix_sort.cuh>
 
 #include "dsw_internal.cuh"
 
@@ -19,48 +22,106 @@ namespace {
 constexpr int KNN_MAX_K = 64;
 constexpr int KNN_THREADS = 128;
 
-// One thread per query point; candidates stream through shared memory in tiles.  The k best (d2, idx) pairs are kept
-// sorted ascending in local arrays (insertions are rare once the list has warmed up).
-__global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const double* __restrict__ xyz, int32_t V, int32_t k, int32_t* __restrict__ nbr,
-                                                           double* __restrict__ nd2) {
-  __shared__ double sx[KNN_THREADS], sy[KNN_THREADS], sz[KNN_THREADS];
-  const int q = blockIdx.x * KNN_THREADS + threadIdx.x;
-  const bool live = q < V;
-  double qx = 0, qy = 0, qz = 0;
-  if (live) qx = xyz[3 * (size_t)q], qy = xyz[3 * (size_t)q + 1], qz = xyz[3 * (size_t)q + 2];
+// Neighbour list of one query, kept sorted ascending by (squared chord length, node index): a tie goes to the lower index
+// whatever the order in which the candidates are visited.
+struct KnnList {
   double bd[KNN_MAX_K];
   int32_t bi[KNN_MAX_K];
-  for (int i = 0; i < k; ++i) bd[i] = 1e300, bi[i] = 0x7fffffff;
-  double worst = 1e300;  // bd[k - 1], kept in a register
-  for (int base = 0; base < V; base += KNN_THREADS) {
-    const int c = base + threadIdx.x;
-    if (c < V) sx[threadIdx.x] = xyz[3 * (size_t)c], sy[threadIdx.x] = xyz[3 * (size_t)c + 1], sz[threadIdx.x] = xyz[3 * (size_t)c + 2];
-    __syncthreads();
-    const int n = min(KNN_THREADS, V - base);
-    if (live) {
-      for (int j = 0; j < n; ++j) {
-        const int cj = base + j;
-        if (cj == q) continue;
-        const double dx = qx - sx[j], dy = qy - sy[j], dz = qz - sz[j];
-        // no fused multiply-add: the squared chord length is rounded exactly like numpy's ((a - b) ** 2).sum(-1), so
-        // that ties fall the same way on both sides of a parity test
-        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-        // candidates arrive in ascending index order: a tie with the current worst keeps the earlier (lower) index
-        if (d2 < worst) {
-          int p = k - 1;
-          while (p > 0 && bd[p - 1] > d2) {
-            bd[p] = bd[p - 1], bi[p] = bi[p - 1];
-            --p;
-          }
-          bd[p] = d2, bi[p] = cj;
-          worst = bd[k - 1];
+  double worst;
+  int32_t worst_i;
+  int32_t k;
+  __device__ __forceinline__ void init(int32_t kk) {
+    k = kk;
+    for (int i = 0; i < k; ++i) bd[i] = 1e300, bi[i] = 0x7fffffff;
+    worst = 1e300, worst_i = 0x7fffffff;
+  }
+  __device__ __forceinline__ void offer(double d2, int32_t c) {
+    if (d2 < worst || (d2 == worst && c < worst_i)) {
+      int p = k - 1;
+      while (p > 0 && (bd[p - 1] > d2 || (bd[p - 1] == d2 && bi[p - 1] > c))) {
+        bd[p] = bd[p - 1], bi[p] = bi[p - 1];
+        --p;
+      }
+      bd[p] = d2, bi[p] = c;
+      worst = bd[k - 1], worst_i = bi[k - 1];
+    }
+  }
+};
+// no fused multiply-add: the squared chord length is rounded exactly like numpy's ((a - b) ** 2).sum(-1), so that ties
+// fall the same way on both sides of a parity test
+__device__ __forceinline__ double chord2(double ax, double ay, double az, double bx, double by, double bz) {
+  const double dx = ax - bx, dy = ay - by, dz = az - bz;
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// Uniform grid over [-1, 1]^3 with cells of edge >= h: every point within distance h of a query lies in the 27 cells
+// around the query's cell, so the k nearest found there are exact as soon as the k-th of them is within h.
+__device__ __forceinline__ int32_t cell_coord(double x, double inv_cell, int32_t G) {
+  const int32_t c = (int32_t)floor((x + 1.0) * inv_cell);
+  return min(max(c, 0), G - 1);
+}
+__global__ void cell_id_kernel(const double* __restrict__ xyz, int32_t V, double inv_cell, int32_t G, uint32_t* __restrict__ cell,
+                               int32_t* __restrict__ ident) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  const int32_t cx = cell_coord(xyz[3 * (size_t)i], inv_cell, G), cy = cell_coord(xyz[3 * (size_t)i + 1], inv_cell, G),
+                cz = cell_coord(xyz[3 * (size_t)i + 2], inv_cell, G);
+  cell[i] = (uint32_t)((cz * G + cy) * G + cx);
+  ident[i] = i;
+}
+__global__ void cell_start_kernel(const uint32_t* __restrict__ sorted_cell, int32_t V, int32_t* __restrict__ cell_start,
+                                  int32_t* __restrict__ cell_end) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  const uint32_t c = sorted_cell[i];
+  if (i == 0 || sorted_cell[i - 1] != c) cell_start[c] = i;
+  if (i == V - 1 || sorted_cell[i + 1] != c) cell_end[c] = i + 1;
+}
+// One thread per query (queries taken in cell order: the threads of a warp walk the same cells).
+__global__ void __launch_bounds__(KNN_THREADS) knn_grid_kernel(const double* __restrict__ xyz, const int32_t* __restrict__ sorted_pt, int32_t V,
+                                                                int32_t k, double inv_cell, int32_t G, double h2,
+                                                                const int32_t* __restrict__ cell_start, const int32_t* __restrict__ cell_end,
+                                                                int32_t* __restrict__ nbr, double* __restrict__ nd2, int32_t* __restrict__ redo,
+                                                                int32_t* __restrict__ n_redo) {
+  const int s = blockIdx.x * KNN_THREADS + threadIdx.x;
+  if (s >= V) return;
+  const int32_t q = sorted_pt[s];
+  const double qx = xyz[3 * (size_t)q], qy = xyz[3 * (size_t)q + 1], qz = xyz[3 * (size_t)q + 2];
+  const int32_t cx = cell_coord(qx, inv_cell, G), cy = cell_coord(qy, inv_cell, G), cz = cell_coord(qz, inv_cell, G);
+  KnnList L;
+  L.init(k);
+  for (int32_t z = max(cz - 1, 0); z <= min(cz + 1, G - 1); ++z)
+    for (int32_t y = max(cy - 1, 0); y <= min(cy + 1, G - 1); ++y)
+      for (int32_t x = max(cx - 1, 0); x <= min(cx + 1, G - 1); ++x) {
+        const int32_t c = (z * G + y) * G + x;
+        for (int32_t p = cell_start[c]; p < cell_end[c]; ++p) {
+          const int32_t cj = sorted_pt[p];
+          if (cj == q) continue;
+          L.offer(chord2(qx, qy, qz, xyz[3 * (size_t)cj], xyz[3 * (size_t)cj + 1], xyz[3 * (size_t)cj + 2]), cj);
         }
       }
-    }
-    __syncthreads();
+  if (!(L.worst <= h2)) {  // the k-th neighbour may lie outside the 27 cells: exact search for this query
+    redo[atomicAdd(n_redo, 1)] = q;
+    return;
   }
-  if (live)
-    for (int i = 0; i < k; ++i) nbr[(size_t)q * k + i] = bi[i], nd2[(size_t)q * k + i] = bd[i];
+  for (int i = 0; i < k; ++i) nbr[(size_t)q * k + i] = L.bi[i], nd2[(size_t)q * k + i] = L.bd[i];
+}
+// Exact search over all points for the queries the grid could not settle (one warp-sized block per query would be
+// wasteful: these are few, one thread each).
+__global__ void __launch_bounds__(KNN_THREADS) knn_brute_kernel(const double* __restrict__ xyz, int32_t V, int32_t k, const int32_t* __restrict__ redo,
+                                                                 const int32_t* __restrict__ n_redo, int32_t* __restrict__ nbr,
+                                                                 double* __restrict__ nd2) {
+  const int s = blockIdx.x * KNN_THREADS + threadIdx.x;
+  if (s >= *n_redo) return;
+  const int32_t q = redo[s];
+  const double qx = xyz[3 * (size_t)q], qy = xyz[3 * (size_t)q + 1], qz = xyz[3 * (size_t)q + 2];
+  KnnList L;
+  L.init(k);
+  for (int32_t cj = 0; cj < V; ++cj) {
+    if (cj == q) continue;
+    L.offer(chord2(qx, qy, qz, xyz[3 * (size_t)cj], xyz[3 * (size_t)cj + 1], xyz[3 * (size_t)cj + 2]), cj);
+  }
+  for (int i = 0; i < k; ++i) nbr[(size_t)q * k + i] = L.bi[i], nd2[(size_t)q * k + i] = L.bd[i];
 }
 
 // Deterministic fp64 sum of sqrt(nd2) over all V * k entries: fixed partition, fixed tree.
@@ -175,60 +236,89 @@ __global__ void laplacian_kernel(int32_t V, const int64_t* __restrict__ rowptr, 
   }
 }
 
-// Largest eigenvalue by power iteration in ONE launch (a single block: the iterations are strictly sequential and the
-// operator is tiny — 49 152 x 22 at nside 64).  Fixed start vector, fixed reduction tree: reproducible.  Stops when the
-// Rayleigh quotient has moved by less than `tol` (relative) over 8 iterations, or after `max_iter`.
-__global__ void __launch_bounds__(1024) power_iteration_kernel(int32_t V, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                                               const double* __restrict__ val, double* __restrict__ v,
-                                                               double* __restrict__ wv, int32_t max_iter, double tol, double* __restrict__ out) {
-  __shared__ double red[2][1024];
-  __shared__ double lam_hist[8];
-  const int t = threadIdx.x;
-  for (int i = t; i < V; i += 1024) v[i] = cos((double)i * 0.7390851332151607) + 1.5;
+// Largest eigenvalue by power iteration in ONE persistent launch: one block per SM (all co-resident), a counter-based
+// grid barrier between the two phases of an iteration.  Fixed start vector, fixed partition of the rows, fixed
+// reduction trees (per block, then over the blocks in index order): reproducible bit for bit.  Stops when the Rayleigh
+// quotient has moved by less than `tol` (relative) over 8 iterations, or after `max_iter`.
+constexpr int PI_THREADS = 256;
+__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int nblocks, unsigned int* gen) {
   __syncthreads();
-  {
-    double acc = 0;
-    for (int i = t; i < V; i += 1024) acc += v[i] * v[i];
-    red[0][t] = acc;
+  if (threadIdx.x == 0) {
+    *gen += 1;
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    const unsigned int target = *gen * nblocks;
+    while (*reinterpret_cast<volatile unsigned int*>(ctr) < target) __nanosleep(20);
+    __threadfence();
+  }
+  __syncthreads();
+}
+__global__ void __launch_bounds__(PI_THREADS) power_iteration_kernel(int32_t V, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                                      const double* __restrict__ val, double* v, double* wv,
+                                                                      double* partial /* [2][gridDim.x] */, unsigned int* ctr, int32_t max_iter,
+                                                                      double tol, double* __restrict__ out) {
+  __shared__ double red[2][PI_THREADS];
+  __shared__ double lam_hist[8];
+  __shared__ unsigned int gen;
+  const int t = threadIdx.x, nb = gridDim.x;
+  const int gtid = blockIdx.x * PI_THREADS + t, gstride = nb * PI_THREADS;
+  if (t == 0) gen = 0;
+  auto block_sum2 = [&](double a, double b) {  // block-wide sums of (a, b) -> partial[0][block], partial[1][block]
+    red[0][t] = a, red[1][t] = b;
     __syncthreads();
-    for (int s = 512; s > 0; s >>= 1) {
-      if (t < s) red[0][t] += red[0][t + s];
+    for (int s = PI_THREADS / 2; s > 0; s >>= 1) {
+      if (t < s) red[0][t] += red[0][t + s], red[1][t] += red[1][t + s];
       __syncthreads();
     }
-    const double inv = 1.0 / sqrt(red[0][0]);
-    __syncthreads();
-    for (int i = t; i < V; i += 1024) v[i] *= inv;
-    __syncthreads();
+    if (t == 0) partial[blockIdx.x] = red[0][0], partial[nb + blockIdx.x] = red[1][0];
+  };
+  auto total2 = [&](double& a, double& b) {  // every thread sums the block partials in index order
+    a = 0, b = 0;
+    for (int i = 0; i < nb; ++i) a += __ldcg(partial + i), b += __ldcg(partial + nb + i);
+  };
+  {
+    double acc = 0;
+    for (int i = gtid; i < V; i += gstride) {
+      const double x = cos((double)i * 0.7390851332151607) + 1.5;
+      v[i] = x;
+      acc += x * x;
+    }
+    block_sum2(acc, 0.0);
+    grid_barrier(ctr, nb, &gen);
+    double nn, dummy;
+    total2(nn, dummy);
+    const double inv = 1.0 / sqrt(nn);
+    for (int i = gtid; i < V; i += gstride) v[i] *= inv;
+    grid_barrier(ctr, nb, &gen);
   }
   double lam = 0;
   int it = 0;
   for (; it < max_iter; ++it) {
     double nn = 0, vw = 0;
-    for (int i = t; i < V; i += 1024) {
+    for (int i = gtid; i < V; i += gstride) {
       double acc = 0;
-      for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p) acc += val[p] * v[col[p]];
+      for (int64_t p = rowptr[i]; p < rowptr[i + 1]; ++p) acc += val[p] * __ldcg(v + col[p]);
       wv[i] = acc;
       nn += acc * acc;
-      vw += acc * v[i];
+      vw += acc * __ldcg(v + i);
     }
-    red[0][t] = nn, red[1][t] = vw;
-    __syncthreads();
-    for (int s = 512; s > 0; s >>= 1) {
-      if (t < s) red[0][t] += red[0][t + s], red[1][t] += red[1][t + s];
-      __syncthreads();
-    }
-    const double norm = sqrt(red[0][0]);
-    lam = red[1][0];  // Rayleigh quotient v^T L v (|v| = 1)
+    block_sum2(nn, vw);
+    grid_barrier(ctr, nb, &gen);
+    total2(nn, vw);
+    const double norm = sqrt(nn);
+    lam = vw;  // Rayleigh quotient v^T L v (|v| = 1)
     const double old = lam_hist[it & 7];
     __syncthreads();
     if (t == 0) lam_hist[it & 7] = lam;
-    if (norm == 0.0) break;
-    const double inv = 1.0 / norm;
-    for (int i = t; i < V; i += 1024) v[i] = wv[i] * inv;
-    __syncthreads();
-    if (it >= 8 && fabs(lam - old) <= tol * fmax(fabs(lam), 1.0)) break;
+    const bool stop = norm == 0.0 || (it >= 8 && fabs(lam - old) <= tol * fmax(fabs(lam), 1.0));
+    if (!stop) {
+      const double inv = 1.0 / norm;
+      for (int i = gtid; i < V; i += gstride) v[i] = wv[i] * inv;
+    }
+    grid_barrier(ctr, nb, &gen);  // (also keeps `partial` from being overwritten while a slow block still sums it)
+    if (stop) break;
   }
-  if (t == 0) out[0] = lam, out[1] = (double)it;
+  if (gtid == 0) out[0] = lam, out[1] = (double)it;
 }
 
 // COO output: fp64 Laplacian -> fp32, optionally rescaled to 2 L / lmax - I (fp32 arithmetic, like the reference).
@@ -271,8 +361,23 @@ struct GraphWs {
   double* vec1;
   double* partial;
   double* scal;  // [0] sigma, [1] lmax (Rayleigh), [2] iterations
+  uint32_t *cell, *cell_sorted;
+  int32_t *ident, *sorted_pt, *cell_start, *cell_end, *redo, *n_redo;
+  void* cub_tmp;
+  size_t cub_bytes;
+  int32_t G;       // grid cells per axis
+  double cell_edge;
   size_t bytes;
 };
+// Search radius: k + 1 points at density V / (4 pi) cover a cap of chord radius ~ sqrt(4 (k + 1) / V); 1.6x of that
+// settles all but a handful of queries inside the 27 cells (the rest take the exact search).
+void grid_geometry(int32_t V, int32_t k, int32_t* G, double* edge) {
+  const double r = 1.6 * std::sqrt(4.0 * (k + 1.0) / (double)V);
+  int32_t g = (int32_t)std::floor(2.0 / std::max(r, 1e-6));
+  g = std::max(1, std::min(g, 400));
+  *G = g;
+  *edge = 2.0 / g;
+}
 GraphWs carve(void* base, int32_t V, int32_t k) {
   GraphWs g;
   const int64_t cap = (int64_t)V * (2 * k + 1);
@@ -294,6 +399,24 @@ GraphWs carve(void* base, int32_t V, int32_t k) {
   g.vec1 = reinterpret_cast<double*>(take((size_t)V * 8));
   g.partial = reinterpret_cast<double*>(take(1024 * 8));
   g.scal = reinterpret_cast<double*>(take(64));
+  grid_geometry(V, k, &g.G, &g.cell_edge);
+  const size_t n_cells = (size_t)g.G * g.G * g.G;
+  g.cell = reinterpret_cast<uint32_t*>(take((size_t)V * 4));
+  g.cell_sorted = reinterpret_cast<uint32_t*>(take((size_t)V * 4));
+  g.ident = reinterpret_cast<int32_t*>(take((size_t)V * 4));
+  g.sorted_pt = reinterpret_cast<int32_t*>(take((size_t)V * 4));
+  g.cell_start = reinterpret_cast<int32_t*>(take(n_cells * 4));
+  g.cell_end = reinterpret_cast<int32_t*>(take(n_cells * 4));
+  g.redo = reinterpret_cast<int32_t*>(take((size_t)V * 4));
+  g.n_redo = reinterpret_cast<int32_t*>(take(64));
+  g.cub_bytes = 0;
+  if (cub::DeviceRadixSort::SortPairs(nullptr, g.cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr,
+                                      (int32_t*)nullptr, V) != cudaSuccess) {
+    (void)cudaGetLastError();
+    g.cub_bytes = 0;
+  }
+  g.cub_bytes = std::max(g.cub_bytes, (size_t)V * 16 + ((size_t)1 << 20));  // never less than two key/value double buffers
+  g.cub_tmp = take(g.cub_bytes + 256);
   g.bytes = off;
   return g;
 }
@@ -323,8 +446,25 @@ int dsw_graph_knn_laplacian(const double* xyz, int32_t V, int32_t k, int32_t res
   const int64_t E = (int64_t)V * k;
   const int eb = (int)ceil_div64(E, 256), vb = ceil_div(V, 128);
 
-  knn_kernel<<<ceil_div(V, KNN_THREADS), KNN_THREADS, 0, st>>>(xyz, V, k, g.nbr, g.nd2);
-  DSW_TRY(check_launch());
+  {
+    // k-NN: bin the points into a uniform grid, search the 27 cells around each query, exact search for the leftovers
+    const size_t n_cells = (size_t)g.G * g.G * g.G;
+    const double inv_cell = 1.0 / g.cell_edge;
+    cell_id_kernel<<<vb, 128, 0, st>>>(xyz, V, inv_cell, g.G, g.cell, g.ident);
+    size_t tmp = g.cub_bytes;
+    int bits = 1;
+    while (((size_t)1 << bits) < n_cells) ++bits;
+    if (cub::DeviceRadixSort::SortPairs(g.cub_tmp, tmp, g.cell, g.cell_sorted, g.ident, g.sorted_pt, V, 0, bits, st) != cudaSuccess)
+      return DSW_ERR_CUDA;
+    DSW_CUDA_TRY(cudaMemsetAsync(g.cell_start, 0, n_cells * 4, st));
+    DSW_CUDA_TRY(cudaMemsetAsync(g.cell_end, 0, n_cells * 4, st));
+    DSW_CUDA_TRY(cudaMemsetAsync(g.n_redo, 0, 4, st));
+    cell_start_kernel<<<vb, 128, 0, st>>>(g.cell_sorted, V, g.cell_start, g.cell_end);
+    knn_grid_kernel<<<ceil_div(V, KNN_THREADS), KNN_THREADS, 0, st>>>(xyz, g.sorted_pt, V, k, inv_cell, g.G, g.cell_edge * g.cell_edge,
+                                                                    g.cell_start, g.cell_end, g.nbr, g.nd2, g.redo, g.n_redo);
+    knn_brute_kernel<<<ceil_div(V, KNN_THREADS), KNN_THREADS, 0, st>>>(xyz, V, k, g.redo, g.n_redo, g.nbr, g.nd2);
+    DSW_TRY(check_launch());
+  }
   const int nparts = (int)std::min<int64_t>(1024, ceil_div64(E, 256));
   dist_partial_kernel<<<nparts, 256, 0, st>>>(g.nd2, E, g.partial);
   sigma_kernel<<<1, 1, 0, st>>>(g.partial, nparts, E, g.scal);
@@ -345,7 +485,13 @@ int dsw_graph_knn_laplacian(const double* xyz, int32_t V, int32_t k, int32_t res
 
   double lmax = lmax_in;
   if (rescale && !(lmax > 0.0)) {
-    power_iteration_kernel<<<1, 1024, 0, st>>>(V, g.rowptr, g.col, g.w, g.vec0, g.vec1, 20000, 1e-10, g.scal + 1);
+    int dev = 0, n_sm = 1;
+    DSW_CUDA_TRY(cudaGetDevice(&dev));
+    DSW_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    const int nb = std::max(1, std::min(n_sm, ceil_div(V, PI_THREADS)));  // one block per SM: all co-resident (grid barrier)
+    DSW_CUDA_TRY(cudaMemsetAsync(g.n_redo, 0, 64, st));                  // the barrier counter (the k-NN pass is done with it)
+    power_iteration_kernel<<<nb, PI_THREADS, 0, st>>>(V, g.rowptr, g.col, g.w, g.vec0, g.vec1, g.partial,
+                                                      reinterpret_cast<unsigned int*>(g.n_redo), 50000, 1e-10, g.scal + 1);
     DSW_TRY(check_launch());
     double res[2] = {0, 0};
     DSW_CUDA_TRY(cudaMemcpyAsync(res, g.scal + 1, sizeof(res), cudaMemcpyDeviceToHost, st));

@@ -64,7 +64,8 @@ def test_device_knn_laplacian_matches_host_restatement(nside, k, dev):
     # rescaled: lmax from the device power iteration vs ARPACK on the host operator
     lap_s, lmax = GD.knn_laplacian_device(xyz, k, dev, rescale=True)
     true = float(sla.eigsh(L, k=1, which="LA", return_eigenvectors=False, tol=1e-12)[0])
-    assert true * (1.01 - 1e-6) <= lmax <= true * (1.01 + 1e-6), (lmax, true)
+    # the Rayleigh quotient approaches lmax from below: converged to 1e-4 (the 1 % margin covers it a hundred times over)
+    assert true * 1.01 * (1.0 - 1e-4) <= lmax <= true * 1.01 * (1.0 + 1e-9), (lmax, true)
     want = G.prepare_torch_laplacian(L, lmax=lmax).coalesce()
     got = lap_s.coalesce()
     assert torch.equal(got.indices().cpu(), want.indices())
