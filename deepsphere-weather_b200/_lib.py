@@ -63,6 +63,8 @@ SIGNATURES = {
     "dsw_nested_avgpool_fwd": (C.c_int, [_ptr, _i64, _i64, _ptr, _i32, _i32, _i32, _i32, _ptr]),
     "dsw_nested_repeat": (C.c_int, [_ptr, _i64, _i64, _ptr, _f32, _i32, _i32, _i32, _i32, _ptr]),
     "dsw_nested_sum": (C.c_int, [_ptr, _i64, _i64, _ptr, _i32, _i32, _i32, _i32, _ptr]),
+    "dsw_ar_stack_fwd": (C.c_int, [_ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _i32, _ptr]),
+    "dsw_ar_stack_bwd": (C.c_int, [_ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _i32, _ptr]),
     "dsw_graph_workspace_bytes": (_sz, [_i32, _i32]),
     "dsw_graph_nnz_capacity": (_i64, [_i32, _i32]),
     "dsw_graph_knn_laplacian": (C.c_int, [_ptr, _i32, _i32, _i32, C.c_double, _i64, _ptr, _ptr, _ptr, C.POINTER(_i64),

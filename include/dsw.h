@@ -270,6 +270,27 @@ enum {
   DSW_OPT_COUNT = 21
 };
 /* ---------------------------------------------------------------------------------------------
+ * Autoregressive input stacking — the step of the training loop right before model(X) (the
+ * reference leaves it to xforecasting.AutoregressiveTraining, scripts_training/train_predict_state.py:392-436, ar_settings
+ * of modules/utils_config.py:82-86):  X[b][t][v][:] = [dyn_t[b][v][0..Fd) | bc_t[b][v][0..Fb) | static[v][0..Fs)]  for the T
+ * input time slots.  Every slot is a POINTER (an observed state or an earlier prediction), so the shifted history is never
+ * materialised: one kernel replaces the shift (cat), the expand of the static fields and the three-way cat.
+ * dsw_ar_stack_bwd writes dX's dynamic channels of every slot with ddyn[t] != NULL to that dense [B][V][Fd] buffer.
+ * ------------------------------------------------------------------------------------------- */
+#define DSW_AR_MAX_SLOTS 8
+typedef struct dsw_ar_slots {
+  const float* dyn[DSW_AR_MAX_SLOTS];  /* slot t: [B][V][Fd], element strides dyn_sB / dyn_sV, unit feature stride */
+  int64_t dyn_sB[DSW_AR_MAX_SLOTS], dyn_sV[DSW_AR_MAX_SLOTS];
+  const float* bc[DSW_AR_MAX_SLOTS];   /* slot t: [B][V][Fb] (ignored when Fb == 0) */
+  int64_t bc_sB[DSW_AR_MAX_SLOTS], bc_sV[DSW_AR_MAX_SLOTS];
+  const float* stat;                   /* [V][Fs] contiguous (ignored when Fs == 0) */
+  float* ddyn[DSW_AR_MAX_SLOTS];       /* backward only: gradient buffer of slot t or NULL */
+} dsw_ar_slots;
+int dsw_ar_stack_fwd(const dsw_ar_slots* slots, float* X, int32_t B, int32_t T, int32_t V, int32_t Fd, int32_t Fb, int32_t Fs, void* stream);
+int dsw_ar_stack_bwd(const dsw_ar_slots* slots, const float* dX, int32_t B, int32_t T, int32_t V, int32_t Fd, int32_t Fb, int32_t Fs,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Device-side construction of the operators that feed the path.
  *
  * dsw_graph_knn_laplacian: symmetrised Gaussian k-NN graph of V unit vectors xyz[V][3] (fp64, device) and its normalised
