@@ -162,7 +162,12 @@ class ARRollout:
     # ---- CUDA graph: the whole rollout (forward x n, losses, backward) as one replay ----
     def capture(self, history, bc, static, targets, zero_grad=None, warmup: int = 3):
         """Record :meth:`step` into a CUDA graph on static copies of the arguments.  Afterwards :meth:`replay` copies new
-        batches into those buffers and replays; parameter gradients land in the same ``p.grad`` tensors every time."""
+        batches into those buffers and replays; parameter gradients land in the same ``p.grad`` tensors every time.
+        (PyTorch's rule for whole-step capture applies: no loss tensor of an earlier, eager step may still be alive —
+        it would keep AccumulateGrad nodes of the default stream in the graph.  :meth:`step` returns a detached loss.)"""
+        import gc
+
+        gc.collect()
         dev = history.device
         self._static = [t.clone() if t is not None else None for t in (history, bc, static, targets)]
         side = torch.cuda.Stream(dev)

@@ -39,7 +39,9 @@ inline bool encode_f32_map(CUtensorMap* out, const float* base, int rank, const 
     static thread_local int bound_device = -1;
     int dev = -1;
     if (cudaGetDevice(&dev) == cudaSuccess && dev != bound_device) {
-      (void)cudaFree(nullptr);
+      // cudaSetDevice (CUDA >= 12) initialises the primary context and makes it current; unlike cudaFree(0) it touches no
+      // stream, so it is legal while another thread's stream capture is in progress (CUDA graphs of a training step)
+      (void)cudaSetDevice(dev);
       bound_device = dev;
     }
   }
@@ -53,7 +55,7 @@ inline bool encode_f32_map(CUtensorMap* out, const float* base, int rank, const 
   if (rc == CUDA_ERROR_INVALID_CONTEXT || rc == CUDA_ERROR_NOT_INITIALIZED) {
     // A thread that has only used the runtime API lazily (PyTorch's autograd worker on its first backward) has no
     // driver context bound yet: bind the device's primary context and encode again.
-    (void)cudaFree(nullptr);
+    (void)cudaSetDevice([] { int d = 0; (void)cudaGetDevice(&d); return d; }());
     rc = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), d, s, b, e,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

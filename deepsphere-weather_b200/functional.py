@@ -69,6 +69,22 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 
 
+# Plans whose Python owner has been garbage-collected.  Their device memory is NOT released from the finaliser: the
+# garbage collector may run at any moment — in particular while another part of the program is capturing a CUDA graph,
+# where cudaFree (an implicitly synchronising call) invalidates the capture.  They are released the next time a plan is
+# built (plan construction synchronises anyway and never happens inside a capture) or by release_dead_plans().
+_DEAD_PLANS: list = []
+
+
+def release_dead_plans() -> int:
+    """Free the device memory of plans whose owners are gone; returns how many were released."""
+    n = 0
+    while _DEAD_PLANS:
+        _lib.load().dsw_plan_destroy(_DEAD_PLANS.pop())
+        n += 1
+    return n
+
+
 class SparsePlan:
     """Device-resident CSR / CSR^T / row-block layouts of one sparse operator (``dsw_plan``).
 
@@ -88,6 +104,7 @@ class SparsePlan:
         self.nnz = int(val.numel())
         self.device = coo.device
         lib = _lib.load()
+        release_dead_plans()
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
             rc = lib.dsw_plan_create(
@@ -96,7 +113,7 @@ class SparsePlan:
             )
         _lib.check(rc, "dsw_plan_create")
         self.handle = handle
-        self._finalizer = weakref.finalize(self, lib.dsw_plan_destroy, handle)
+        self._finalizer = weakref.finalize(self, _DEAD_PLANS.append, handle)
 
     @property
     def operand_bytes(self) -> int:
