@@ -357,6 +357,47 @@ def time_torch_cuda_baseline(device, steps=5, warmup=2):
             "what": "same U-Net, same step, torch-CUDA path of the reference arithmetic (cuSPARSE + cuBLAS fp32) on this GPU, B 32"}
 
 
+def time_ar_rollout(device, steps=5):
+    """The autoregressive training step of the reference's loop (xforecasting.AutoregressiveTraining with ar_iterations = 2:
+    three forward passes with the predictions fed back, WeightedMSELoss per iteration, one backward) on cfg3's model at 8
+    samples — the small-batch regime of the 8-GPU run — eager and replayed from one CUDA graph."""
+    from deepsphere_weather_b200.ar import ARRollout
+    from deepsphere_weather_b200.ddp import FlatGradBucket
+    from deepsphere_weather_b200.losses import WeightedMSELoss
+
+    B, T, Fd, Fb, Fs, ar_it = 8, 3, 2, 1, 4, 2
+    model, V = build_model(device)
+    bucket = FlatGradBucket(model)
+    crit = WeightedMSELoss(weights=torch.rand(V, device=device) + 0.5)
+    roll = ARRollout(model, crit, ar_it)
+    mk = lambda *s: torch.randn(*s, device=device)
+    args = (mk(B, T, V, Fd), mk(B, T + ar_it + 1, V, Fb), mk(V, Fs), mk(B, ar_it + 1, V, Fd))
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / steps
+
+    t_eager = timed(lambda: roll.step(*args, zero_grad=bucket.zero_))
+    res = {"workload": f"AR rollout: cfg3 model, B {B}, ar_iterations {ar_it} (3 forward passes), WeightedMSELoss, one backward",
+           "eager_ms_per_step": t_eager * 1e3, "eager_samples_per_s": B / t_eager}
+    try:
+        roll.capture(*args, zero_grad=bucket.zero_)
+        t_graph = timed(lambda: roll.replay(*args))
+        res.update({"cuda_graph_ms_per_step": t_graph * 1e3, "cuda_graph_samples_per_s": B / t_graph})
+    except Exception as exc:
+        res["cuda_graph_error"] = repr(exc)[:200]
+        torch.cuda.synchronize()
+    return res
+
+
 def time_cfg4_strong(device, rank, world, steps, lib):
     """BASELINE.json configs[3] / north star: UNetSpherical nside 64 (49 152 nodes), K 4, GLOBAL batch 64 sharded over the
     ranks (64 / 32 / 16 / 8 samples per GPU at N = 1 / 2 / 4 / 8): strong scaling.  Forward + backward are replayed from a
@@ -592,6 +633,10 @@ def run_ours(args):
             line["nodes_channels_per_s"] = line["cfg2_convcheb"]["nodes_channels_per_s_fwd"]
         except Exception as exc:  # never lose the headline line
             line["roofline"] = {"error": repr(exc)}
+        try:
+            line["ar_rollout"] = time_ar_rollout(device)
+        except Exception as exc:
+            line["ar_rollout"] = {"error": repr(exc)[:200]}
         try:
             line["cfg5_equiangular"] = time_cfg5(device, hbm_gbs)
         except Exception as exc:
