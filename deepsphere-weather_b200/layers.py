@@ -30,7 +30,12 @@ _LINEAR_LIKE = {"linear", "hardshrink ", "sigmoid", "hardsigmoid", "tanh", "hard
 
 
 def convert_to_torch_sparse(mat) -> torch.Tensor:
-    """scipy sparse -> coalesced torch COO (reference ``layers.py:584-594``)."""
+    """scipy sparse -> coalesced torch COO (reference ``layers.py:584-594``).  A torch sparse tensor — e.g. an operator
+    built on the device by ``graphs_device`` — is taken as it is."""
+    if torch.is_tensor(mat):
+        if not mat.is_sparse:
+            raise TypeError("expected a scipy sparse matrix or a torch sparse COO tensor")
+        return mat.coalesce().to(torch.get_default_dtype())
     return scipy_to_torch_coo(mat, torch.get_default_dtype())
 
 
