@@ -306,18 +306,19 @@ class GeneralMaxValUnpool(RemapBlock):
 # Factories                                                       reference layers.py:1139-1242
 # ------------------------------------------------------------------------------------------
 
+from .layers_equiangular import (EQUIANGULAR_POOL, Conv2dEquiangular, EquiangularAvgPool, EquiangularAvgUnpool,  # noqa: E402,F401
+                                 EquiangularMaxPool, EquiangularMaxUnpool)
+
 HEALPIX_POOL = {"max": (HealpixMaxPool, HealpixMaxUnpool), "avg": (HealpixAvgPool, HealpixAvgUnpool)}
-ALL_POOL = {"healpix": HEALPIX_POOL}
+EQUIANGULAR_POOl = EQUIANGULAR_POOL  # (the reference's spelling, layers.py:1144)
+ALL_POOL = {"healpix": HEALPIX_POOL, "equiangular": EQUIANGULAR_POOL}
 
 
 class PoolUnpoolBlock(torch.nn.Module):
     @staticmethod
     def getPoolUnpoolLayer(sampling: str, pool_method: str, **kwargs):
         sampling, pool_method = sampling.lower(), pool_method.lower()
-        if sampling not in ALL_POOL:
-            raise NotImplementedError(
-                f"index pools for sampling '{sampling}' are outside the graph hot path (SURVEY.md §8f rank 4)"
-            )
+        assert sampling in ("healpix", "equiangular")
         assert pool_method in ("max", "avg")
         pool, unpool = ALL_POOL[sampling][pool_method]
         return pool(**kwargs), unpool(**kwargs)
@@ -341,18 +342,22 @@ class PoolUnpoolBlock(torch.nn.Module):
 
 
 def get_conv_fun(conv_type):
-    if conv_type != "graph":
-        raise NotImplementedError("only the graph convolution is on the B200 hot path")
-    return ConvCheb
+    """``{"image": Conv2dEquiangular, "graph": ConvCheb}`` (reference ``layers.py:1198-1201``)."""
+    return {"image": Conv2dEquiangular, "graph": ConvCheb}[conv_type]
 
 
 class GeneralConvBlock(torch.nn.Module):
     @staticmethod
     def getConvLayer(in_channels: int, out_channels: int, kernel_size: int, conv_type: str = "graph", **kwargs):
+        """The layer for ``conv_type`` with the reference's keyword routing (``layers.py:1212-1242``)."""
         conv_type = conv_type.lower()
-        if conv_type != "graph":
-            raise ValueError("{} conv_type is not supported. Choose 'graph'".format(conv_type))
-        assert "laplacian" in kwargs
-        kwargs.pop("lonlat_ratio", None)
-        kwargs.pop("periodic_padding", None)
-        return ConvCheb(in_channels, out_channels, kernel_size, **kwargs)
+        if conv_type == "graph":
+            assert "laplacian" in kwargs
+            kwargs.pop("lonlat_ratio", None)
+            kwargs.pop("periodic_padding", None)
+            return get_conv_fun(conv_type)(in_channels, out_channels, kernel_size, **kwargs)
+        if conv_type == "image":
+            assert "lonlat_ratio" in kwargs
+            kwargs.pop("laplacian", None)
+            return get_conv_fun(conv_type)(in_channels, out_channels, kernel_size, **kwargs)
+        raise ValueError("{} conv_type is not supported. Choose either 'graph' or 'image'".format(conv_type))

@@ -48,12 +48,18 @@ class ConvBlock(torch.nn.Module):
                  batch_norm=False, batch_norm_before_activation=False, activation=True, activation_fun="relu",
                  periodic_padding=True, lonlat_ratio=2, backend=None):
         super().__init__()
-        if conv_type != "graph":
-            raise NotImplementedError("only conv_type='graph' is on the B200 hot path")
         backend = backend or _default_backend()
         if batch_norm:
             bias = False
-        self.conv = backend.ConvCheb(in_channels, out_channels, kernel_size, laplacian=laplacian, bias=bias)
+        if conv_type == "graph":
+            self.conv = backend.ConvCheb(in_channels, out_channels, kernel_size, laplacian=laplacian, bias=bias)
+        elif conv_type == "image":  # the reference's dense lat x lon convolution (cuDNN)
+            from .layers_equiangular import Conv2dEquiangular
+
+            self.conv = Conv2dEquiangular(in_channels, out_channels, kernel_size, lonlat_ratio=lonlat_ratio,
+                                          periodic_padding=periodic_padding, bias=bias)
+        else:
+            raise ValueError("{} conv_type is not supported. Choose either 'graph' or 'image'".format(conv_type))
         if batch_norm:
             self.bn = torch.nn.BatchNorm1d(out_channels)
         self.bn_before_act = batch_norm_before_activation
@@ -186,16 +192,22 @@ class UNetSpherical(torch.nn.Module):
 
         sampling = sampling.lower()
         pool_method = pool_method.lower()
-        if conv_type.lower() != "graph":
-            raise NotImplementedError("only conv_type='graph' is on the B200 hot path")
+        conv_type = conv_type.lower()
+        if conv_type not in ("graph", "image"):
+            raise ValueError("{} conv_type is not supported. Choose either 'graph' or 'image'".format(conv_type))
+        if conv_type == "image" and sampling != "equiangular":
+            raise ValueError("conv_type='image' needs the equiangular sampling")
         if graph_type != "knn" and laplacians is None:
             raise NotImplementedError("voronoi (cotan) Laplacians need igl; pass laplacians=[...] instead")
         if skip_connection not in ("none", "stack", "sum", "avg", None):
             raise ValueError("'skip_connection' must be one of ('none', 'stack', 'sum', 'avg')")
 
-        cb_kwargs = dict(kernel_size=kernel_size_conv, conv_type="graph", bias=bias, batch_norm=batch_norm,
+        lonlat_ratio = None
+        if sampling == "equiangular":  # reference my_models_graph.py:376-384
+            lonlat_ratio = sampling_kwargs["nlon"] // sampling_kwargs["nlat"]
+        cb_kwargs = dict(kernel_size=kernel_size_conv, conv_type=conv_type, bias=bias, batch_norm=batch_norm,
                          batch_norm_before_activation=batch_norm_before_activation, activation=activation,
-                         activation_fun=activation_fun, periodic_padding=periodic_padding, lonlat_ratio=None,
+                         activation_fun=activation_fun, periodic_padding=periodic_padding, lonlat_ratio=lonlat_ratio,
                          backend=backend)
 
         depth = 3  # hard-coded in the reference (my_models_graph.py:374)
@@ -203,6 +215,10 @@ class UNetSpherical(torch.nn.Module):
         level_kwargs = [dict(sampling_kwargs, k=knn)]
         for _ in range(1, depth):
             level_kwargs.append(_coarsen(sampling, level_kwargs[-1], factor))
+        if laplacians is None and conv_type == "image":
+            # the image convolution has no use for a graph: identity operators keep the attribute and the buffers' shapes
+            sizes = [kw["nlat"] * kw["nlon"] for kw in level_kwargs]
+            laplacians = [G.scipy_to_torch_coo(__import__("scipy.sparse", fromlist=["identity"]).identity(n, format="coo")) for n in sizes]
         if laplacians is None:
             laplacians = [
                 G.prepare_torch_laplacian(G.knn_laplacian(_graph_xyz(sampling, kw), knn)) for kw in level_kwargs
@@ -220,11 +236,18 @@ class UNetSpherical(torch.nn.Module):
             self.pool1, self.unpool1 = backend.general_pools(pool_method=pool_method, matrices=pool_matrices[0])
             self.pool2, self.unpool2 = backend.general_pools(pool_method=pool_method, matrices=pool_matrices[1])
         elif pool_method in ("max", "avg"):
-            if sampling != "healpix":
-                raise NotImplementedError("index pools are implemented for nested HEALPix only")
-            pool_cls, unpool_cls = backend.healpix_pools[pool_method]
-            self.pool1, self.unpool1 = pool_cls(kernel_size=kernel_size_pooling), unpool_cls(kernel_size=kernel_size_pooling)
-            self.pool2, self.unpool2 = pool_cls(kernel_size=kernel_size_pooling), unpool_cls(kernel_size=kernel_size_pooling)
+            if sampling == "healpix":
+                pool_cls, unpool_cls = backend.healpix_pools[pool_method]
+                pkw = dict(kernel_size=kernel_size_pooling)
+            elif sampling == "equiangular":  # dense 2-D index pools (torch ops)
+                from .layers_equiangular import EQUIANGULAR_POOL
+
+                pool_cls, unpool_cls = EQUIANGULAR_POOL[pool_method]
+                pkw = dict(kernel_size=kernel_size_pooling, lonlat_ratio=lonlat_ratio)
+            else:
+                raise NotImplementedError("index pools exist for the nested HEALPix and the equiangular samplings only")
+            self.pool1, self.unpool1 = pool_cls(**pkw), unpool_cls(**pkw)
+            self.pool2, self.unpool2 = pool_cls(**pkw), unpool_cls(**pkw)
         else:
             raise ValueError("Not valid pooling method provided.")
 

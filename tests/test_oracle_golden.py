@@ -179,3 +179,70 @@ def test_reshape_tensors_4_loss_matches_reference_golden():
     y = torch.from_numpy(g["reshape_in"])
     a, b = reshape_tensors_4_loss(y, y + 1, {"sample": 0, "time": 1, "node": 2, "feature": 3})
     assert torch.equal(a, torch.from_numpy(g["reshape_out"])) and torch.equal(b, a + 1)
+
+
+# ----------------------------------------------------------------------------------------------
+# Equiangular image path: the thin torch mirrors against the unmodified reference
+# ----------------------------------------------------------------------------------------------
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="the unmodified reference is only present in the build container")
+@pytest.mark.parametrize("periodic", [True, False])
+def test_equiangular_image_layers_match_the_reference(periodic):
+    import torch
+
+    from deepsphere_weather_b200 import layers_equiangular as E
+
+    ref_layers, _ = ref_import.load_reference()
+    torch.manual_seed(3)
+    n_lat, n_lon, B, Fin, Fout = 8, 16, 2, 5, 7
+    x = torch.randn(B, n_lat * n_lon, Fin)
+    ref = ref_layers.Conv2dEquiangular(Fin, Fout, 3, lonlat_ratio=2, periodic_padding=periodic, bias=True)
+    ours = E.Conv2dEquiangular(Fin, Fout, 3, lonlat_ratio=2, periodic_padding=periodic, bias=True)
+    assert list(ref.state_dict()) == list(ours.state_dict())
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    assert torch.allclose(ours(x), ref(x), atol=1e-6)
+    for tag in ("max", "avg"):
+        rp, ru = (cls(lonlat_ratio=2, kernel_size=4) for cls in ref_layers.ALL_POOL["equiangular"][tag])
+        op, ou = (cls(lonlat_ratio=2, kernel_size=4) for cls in E.EQUIANGULAR_POOL[tag])
+        (yr, ir), (yo, io) = rp(x), op(x)
+        assert torch.equal(yo, yr) and (ir is None) == (io is None) and (ir is None or torch.equal(io, ir))
+        assert torch.equal(ou(yo, io), ru(yr, ir))
+
+
+@pytest.mark.skipif(not ref_import.reference_available(), reason="the unmodified reference is only present in the build container")
+@pytest.mark.parametrize("pool_method", ["max", "avg"])
+def test_image_unet_matches_the_reference_on_the_equiangular_grid(pool_method):
+    """conv_type="image" + equiangular index pools: the whole reference architecture on the dense lat x lon path."""
+    import torch
+
+    _, ref_models = ref_import.load_reference()
+    nlat, nlon, B = 16, 32, 2
+    V = nlat * nlon
+    kw = dict(kernel_size_conv=3, conv_type="image", pool_method=pool_method, periodic_padding=True)
+    args = (M.default_tensor_info(V), "equiangular", {"nlat": nlat, "nlon": nlon})
+    ref = ref_models.UNetSpherical(*args, **kw)
+    # the image path is plain PyTorch and runs on the CPU too; the ResBlock tail then has to be the reference's own
+    # (torch.nn.Linear + in-place ops) instead of the CUDA-only fused kernels of the default backend
+    from types import SimpleNamespace
+
+    from deepsphere_weather_b200 import layers as L
+
+    backend = SimpleNamespace(ConvCheb=L.ConvCheb, healpix_pools={}, general_pools=L.PoolUnpoolBlock.getGeneralPoolUnpoolLayer)
+    ours = M.UNetSpherical(*args, backend=backend, **kw)
+    sd = {k: v for k, v in ref.state_dict().items() if not v.is_sparse}
+    missing = ours.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys and all("laplacian" in k for k in missing.missing_keys)
+    torch.manual_seed(0)
+    with torch.no_grad():
+        for m in (ref, ours):
+            for n, p in m.named_parameters():
+                if n.endswith("rezero_weight"):
+                    p.fill_(0.7)
+    x = torch.randn(B, 3, V, 7)
+    yr, yo = ref(x), ours(x)
+    assert torch.allclose(yo, yr, rtol=1e-5, atol=1e-6)
+    yr.square().mean().backward()
+    yo.square().mean().backward()
+    for (n, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()):
+        assert torch.allclose(p.grad, q.grad, rtol=1e-4, atol=1e-7), n
