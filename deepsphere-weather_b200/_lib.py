@@ -43,6 +43,8 @@ SIGNATURES = {
     "dsw_linear_fwd": (C.c_int, [_ptr, _i64, _i64, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _sz, _ptr]),
     "dsw_linear_bwd": (C.c_int, [_ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _sz, _ptr]),
     "dsw_linear_rezero_fwd": (C.c_int, [_ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _sz, _ptr]),
+    "dsw_linear_bwd_acc": (C.c_int, [_ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _sz, _ptr]),
+    "dsw_linear_rezero_fwd_ld": (C.c_int, [_ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _i32, _i32, _ptr, _sz, _ptr]),
     "dsw_rezero_fwd": (C.c_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
     "dsw_rezero_bwd_workspace_bytes": (_sz, []),
     "dsw_rezero_bwd": (C.c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _sz, _i64, _ptr]),
@@ -53,6 +55,8 @@ SIGNATURES = {
     "dsw_wmse_none_bwd": (C.c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _ptr]),
     "dsw_spmm_fwd": (C.c_int, [_ptr, _ptr, _i64, _i64, _ptr, _i32, _i32, _ptr]),
     "dsw_spmm_bwd": (C.c_int, [_ptr, _ptr, _i64, _i64, _ptr, _i32, _i32, _ptr]),
+    "dsw_spmm_fwd_ex": (C.c_int, [_ptr, _ptr, _i64, _i64, _ptr, _i64, _i64, _ptr, _i64, _i64, _i32, _i32, _ptr]),
+    "dsw_spmm_bwd_ex": (C.c_int, [_ptr, _ptr, _i64, _i64, _ptr, _i64, _i64, _ptr, _i64, _i64, _i32, _i32, _ptr]),
     "dsw_maxval_pool_fwd": (C.c_int, [_ptr, _ptr, _i64, _i64, _ptr, _ptr, _ptr, _i32, _i32, _ptr]),
     "dsw_maxval_pool_bwd": (C.c_int, [_ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr]),
     "dsw_scatter_unpool_fwd": (C.c_int, [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr]),

@@ -90,14 +90,21 @@ int dsw_linear_fwd(const float* x, int64_t x_sB, int64_t x_sV, const float* Wl, 
 int dsw_linear_rezero_fwd(const float* x, int64_t x_sB, int64_t x_sV, const float* Wl, const float* bias, const float* conv_out,
                           const float* scale, float* y, int32_t B, int32_t V, int32_t Fin, int32_t Fout, void* workspace,
                           size_t workspace_bytes, void* stream) {
-  if (!x || !Wl || !y || !conv_out || !scale || B <= 0 || V <= 0 || Fin <= 0 || Fout <= 0) return DSW_ERR_BAD_ARGUMENT;
+  return dsw_linear_rezero_fwd_ld(x, x_sB, x_sV, Wl, bias, conv_out, scale, y, Fout, B, V, Fin, Fout, workspace, workspace_bytes,
+                                  stream);
+}
+
+int dsw_linear_rezero_fwd_ld(const float* x, int64_t x_sB, int64_t x_sV, const float* Wl, const float* bias, const float* conv_out,
+                             const float* scale, float* y, int64_t y_ld, int32_t B, int32_t V, int32_t Fin, int32_t Fout,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x || !Wl || !y || !conv_out || !scale || B <= 0 || V <= 0 || Fin <= 0 || Fout <= 0 || y_ld < Fout) return DSW_ERR_BAD_ARGUMENT;
   if (!workspace || workspace_bytes < dsw_linear_workspace_bytes(B, V, Fin, Fout)) return DSW_ERR_WORKSPACE;
   const LinLayout L = lin_layout((int64_t)B * V, Fin, Fout);
   MixArgs m;
   m.P = 1, m.Ka = Fin, m.rows_per_batch = V, m.N = (int64_t)B * V;
   m.A[0] = x, m.a_sB[0] = x_sB, m.a_sV[0] = x_sV;
   m.Bm = Wl, m.sBp = 0, m.sBk = 1, m.sBc0 = Fin, m.sBc1 = 0;
-  m.bias = bias, m.bias_n = Fout, m.C = y, m.sCp = 0, m.ldc = Fout, m.Cw = Fout, m.Nc = Fout, m.act = 0;
+  m.bias = bias, m.bias_n = Fout, m.C = y, m.sCp = 0, m.ldc = y_ld, m.Cw = Fout, m.Nc = Fout, m.act = 0;
   m.R = conv_out, m.ldr = Fout, m.r_scale = scale;  // y = x . Wl^T + bias + scale * conv_out
   return lin_mix(m, workspace, L.prep_bytes, static_cast<cudaStream_t>(stream));
 }
@@ -105,7 +112,13 @@ int dsw_linear_rezero_fwd(const float* x, int64_t x_sB, int64_t x_sV, const floa
 int dsw_linear_bwd(const float* x, int64_t x_sB, int64_t x_sV, const float* dy, const float* Wl, float* dx, float* dW,
                    float* dbias, int32_t B, int32_t V, int32_t Fin, int32_t Fout, void* workspace, size_t workspace_bytes,
                    void* stream) {
-  if (!dy || B <= 0 || V <= 0 || Fin <= 0 || Fout <= 0) return DSW_ERR_BAD_ARGUMENT;
+  return dsw_linear_bwd_acc(x, x_sB, x_sV, dy, Wl, nullptr, dx, dW, dbias, B, V, Fin, Fout, workspace, workspace_bytes, stream);
+}
+
+int dsw_linear_bwd_acc(const float* x, int64_t x_sB, int64_t x_sV, const float* dy, const float* Wl, const float* dx_addend,
+                       float* dx, float* dW, float* dbias, int32_t B, int32_t V, int32_t Fin, int32_t Fout, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  if (!dy || B <= 0 || V <= 0 || Fin <= 0 || Fout <= 0 || (dx_addend && !dx)) return DSW_ERR_BAD_ARGUMENT;
   if ((dx && !Wl) || (dW && !x)) return DSW_ERR_BAD_ARGUMENT;
   if (!workspace || workspace_bytes < dsw_linear_workspace_bytes(B, V, Fin, Fout)) return DSW_ERR_WORKSPACE;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -119,6 +132,7 @@ int dsw_linear_bwd(const float* x, int64_t x_sB, int64_t x_sV, const float* dy, 
     // dx[n][f] = sum_o dy[n][o] Wl[o][f]: reduction index o -> stride Fin, column f -> stride 1
     m.Bm = Wl, m.sBp = 0, m.sBk = Fin, m.sBc0 = 1, m.sBc1 = 0;
     m.bias = nullptr, m.C = dx, m.sCp = 0, m.ldc = Fin, m.Cw = Fin, m.Nc = Fin, m.act = 0;
+    m.R = dx_addend, m.ldr = Fin;  // dx = dy . Wl + dx_addend (the convolution branch's input gradient)
     DSW_TRY(lin_mix(m, ws, L.prep_bytes, st));
   }
   if (dW) {

@@ -636,17 +636,52 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
     const bool vec_ok = (a.Cw % 4 == 0) && (a.ldc % 4 == 0) && (a.sCp % 4 == 0) &&
                         ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0);
     const int half = lane >> 4, c4 = lane & 15;  // store phase: two rows per instruction, 16 lanes x float4 per row
+    // ADDEND: the epilogue is bound by the latency of its addend loads (short-K mixes: 8 KB in flight per SM).  Each warp
+    // pulls the addend rows of its NEXT tile into L2 a whole tile ahead (one row per lane, a 128-byte line per prefetch).
+    auto prefetch_addend = [&](int64_t lt_next) {
+      if (!ADDEND || a.R == nullptr || lt_next >= my_tiles || (P.dbg & 1024)) return;
+      const int64_t tile_n = blockIdx.x + lt_next * gridDim.x;
+      const int64_t n = (tile_n / n_ctiles) * BM + quarter * 32 + lane;
+      const int c0 = (int)(tile_n % n_ctiles) * BN;
+      if (n >= a.N) return;
+      const float* p = a.R + n * a.ldr + c0;
+      const int ncols = min(BN, a.Nc - c0);
+      for (int c = 0; c < ncols; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + c));
+    };
+    prefetch_addend(0);
     for (int64_t lt = 0; lt < my_tiles; ++lt) {
       const int64_t tile = blockIdx.x + lt * gridDim.x;
       const int buf = (int)(lt & 1);
       const uint32_t ph = (uint32_t)(lt >> 1) & 1;
       const int ctile = (int)(tile % n_ctiles);
       const int64_t row0 = (tile / n_ctiles) * BM + quarter * 32;  // first output row of this warp
+      prefetch_addend(lt + 1);
       mbar_wait(acc_full(buf), ph);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)(buf * P.tmem_cols) + ((uint32_t)(quarter * 32) << 16);
       for (int cg = 0; cg < BN; cg += 64) {
         const int ncol = min(64, BN - cg);  // multiple of 16 (warp-uniform)
+        // columns of this lane in the store phase
+        const int col = ctile * BN + cg + c4 * 4;
+        const bool col_ok = (c4 * 4 < ncol) && (col < a.Nc);
+        // ADDEND: the 16 addend row segments of this lane are loaded in two batches of 8 that are in flight while the
+        // accumulator chunk moves TMEM -> shared memory (first batch) and while the first batch is consumed (second)
+        float4 rv[16];
+        bool addend_vec = false;
+        const float* r_row = nullptr;
+        if (ADDEND) {
+          const int ccol0 = col % a.Cw;
+          addend_vec = col_ok && a.R != nullptr && vec_ok && (col + 3 < a.Nc) && (ccol0 + 3 < a.Cw) && (a.ldr % 4 == 0) &&
+                       ((reinterpret_cast<uintptr_t>(a.R) & 15) == 0);
+          if (addend_vec) {
+            r_row = a.R + (row0 + half) * a.ldr + col;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (row0 + half + 2 * i < a.N) rv[i] = __ldg(reinterpret_cast<const float4*>(r_row + (int64_t)(2 * i) * a.ldr));
+            }
+          }
+        }
         // TMEM loads two chunks (32 columns) at a time, one wait per pair
 #pragma unroll
         for (int hq = 0; hq < 2; ++hq) {
@@ -665,9 +700,6 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
             }
         }
         __syncwarp();
-        // columns of this lane in the store phase
-        const int col = ctile * BN + cg + c4 * 4;
-        const bool col_ok = (c4 * 4 < ncol) && (col < a.Nc);
         if (col_ok) {
           float bv[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -677,39 +709,34 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
           const bool vec = vec_ok && (col + 3 < a.Nc) && (ccol + 3 < a.Cw);
           float* cbase = a.C + (int64_t)cp * a.sCp + ccol;
           const bool relu = a.act == 1;
-          if (ADDEND && vec && a.R != nullptr) {
-            // same, plus the addend row segments (C += r_scale * R): their global loads are issued first
+          if (ADDEND && addend_vec) {
+            // same, plus the addend row segments (C += r_scale * R)
             const float rs = a.r_scale ? __ldg(a.r_scale) : 1.f;
-            const bool r_vec = (a.ldr % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.R) & 15) == 0);
             float* cp_row = cbase + (row0 + half) * a.ldc;
-            const float* r_row = a.R + (row0 + half) * a.ldr + col;
-            const int64_t step = 2 * (int64_t)a.ldc, rstep = 2 * a.ldr;
+            const int64_t step = 2 * (int64_t)a.ldc;
             int64_t n = row0 + half;
 #pragma unroll
-            for (int i0 = 0; i0 < 16; i0 += 4) {
-              float4 rv[4], v[4];
+            for (int i = 8; i < 16; ++i) {  // second batch of addend loads
+              rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (row0 + half + 2 * i < a.N) rv[i] = __ldg(reinterpret_cast<const float4*>(r_row + (int64_t)(2 * i) * a.ldr));
+            }
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (n + 2 * i < a.N) {
-                  const float* rp = r_row + i * rstep;
-                  rv[i] = r_vec ? __ldg(reinterpret_cast<const float4*>(rp)) : make_float4(__ldg(rp), __ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3));
-                }
-              }
+            for (int i0 = 0; i0 < 16; i0 += 4) {
+              float4 v[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(stg + epi_off(2 * (i0 + i) + half, c4));
 #pragma unroll
               for (int i = 0; i < 4; ++i, n += 2, cp_row += step) {
                 if (n >= a.N) continue;
                 float4 o = v[i];
-                o.x = fmaf(rs, rv[i].x, o.x + bv[0]), o.y = fmaf(rs, rv[i].y, o.y + bv[1]);
-                o.z = fmaf(rs, rv[i].z, o.z + bv[2]), o.w = fmaf(rs, rv[i].w, o.w + bv[3]);
+                const float4 r4 = rv[i0 + i];
+                o.x = fmaf(rs, r4.x, o.x + bv[0]), o.y = fmaf(rs, r4.y, o.y + bv[1]);
+                o.z = fmaf(rs, r4.z, o.z + bv[2]), o.w = fmaf(rs, r4.w, o.w + bv[3]);
                 if (relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
                 *reinterpret_cast<float4*>(cp_row) = o;
               }
-              r_row += 4 * rstep;
             }
-          } else if (vec) {
+          } else if (vec && !(ADDEND && a.R != nullptr)) {
             // two phases per 16 rows so that 8 shared-memory reads, then 8 row-segment stores, overlap
             float* cp_row = cbase + (row0 + half) * a.ldc;
             const int64_t step = 2 * (int64_t)a.ldc;
@@ -827,7 +854,7 @@ int launch_mix_tc_ws(const MixArgs& a, void* prep, size_t prep_bytes, bool do_pr
   P.m = a;
   P.BN = std::min(mix_bn_max(), (a.Nc + 15) / 16 * 16);
   P.nkb = (a.Ka + tc::BKB - 1) / tc::BKB;
-  P.dbg = (int)g_options[DSW_OPT_DEBUG].load(std::memory_order_relaxed) & 0x1F0;
+  P.dbg = (int)g_options[DSW_OPT_DEBUG].load(std::memory_order_relaxed) & 0x5F0;
   P.cmode = split_mode();
   int cols = 32;
   while (cols < P.BN) cols <<= 1;

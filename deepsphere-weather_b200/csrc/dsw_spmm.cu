@@ -913,4 +913,28 @@ int dsw_spmm_bwd(const dsw_plan* mat, const float* dy, int64_t dy_sB, int64_t dy
   return launch_hop(mat->tr, mat->tr_rb, a, static_cast<cudaStream_t>(stream));
 }
 
+// Strided-output / accumulating forms (the skip concatenation of the U-Net without a cat: the unpool writes its rows
+// straight into one half of the [B, V, 2C] buffer the decoder reads; the pool's backward adds the skip gradient).
+int dsw_spmm_fwd_ex(const dsw_plan* mat, const float* x, int64_t x_sB, int64_t x_sV, const float* addend, int64_t a_sB,
+                    int64_t a_sV, float* y, int64_t y_sB, int64_t y_sV, int32_t B, int32_t F, void* stream) {
+  if (!mat || !x || !y || B <= 0 || F <= 0 || y_sV < F) return DSW_ERR_BAD_ARGUMENT;
+  HopArgs a;
+  a.X = x, a.x_sB = x_sB, a.x_sV = x_sV;
+  a.G = addend, a.g_sB = a_sB, a.g_sV = a_sV;
+  a.O = y, a.o_sV = y_sV, a.o_sB = y_sB;
+  a.B = B, a.F = F;
+  return launch_hop(mat->fwd, mat->fwd_rb, a, static_cast<cudaStream_t>(stream));
+}
+
+int dsw_spmm_bwd_ex(const dsw_plan* mat, const float* dy, int64_t dy_sB, int64_t dy_sV, const float* addend, int64_t a_sB,
+                    int64_t a_sV, float* dx, int64_t dx_sB, int64_t dx_sV, int32_t B, int32_t F, void* stream) {
+  if (!mat || !dy || !dx || B <= 0 || F <= 0 || dx_sV < F) return DSW_ERR_BAD_ARGUMENT;
+  HopArgs a;
+  a.X = dy, a.x_sB = dy_sB, a.x_sV = dy_sV;
+  a.G = addend, a.g_sB = a_sB, a.g_sV = a_sV;
+  a.O = dx, a.o_sV = dx_sV, a.o_sB = dx_sB;
+  a.B = B, a.F = F;
+  return launch_hop(mat->tr, mat->tr_rb, a, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -373,33 +373,91 @@ def rezero_residual(conv_out, skip, weight):
     return RezeroResidualFunction.apply(conv_out, skip, weight)
 
 
+class _ForkState:
+    """Hand-over between a ResBlock's tail and its ``ForkFunction`` node (see ``fork``)."""
+
+    __slots__ = ("g", "w")
+
+    def __init__(self):
+        self.g = None
+        self.w = None
+
+
+class ForkFunction(torch.autograd.Function):
+    """Identity on the way in; on the way back it finishes the ResBlock's input gradient.  A ResBlock's input feeds the
+    convolution branch and the skip connection (``my_models_graph.py:205-215``), so autograd would add two gradients in a
+    separate element-wise pass.  Here the tail (``LinearRezeroFunction``) leaves its output gradient ``g`` in ``state``
+    instead of computing the skip's input gradient, and this node — which runs once the convolution branch's gradient has
+    arrived — computes ``dx = g . Wl + d_conv`` in the channel-mix epilogue (``dsw_linear_bwd_acc``)."""
+
+    @staticmethod
+    def forward(ctx, x, state: _ForkState):
+        ctx.state = state
+        return x.as_strided(x.shape, x.stride(), x.storage_offset())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, d):
+        st = ctx.state
+        g, w = st.g, st.w
+        st.g = st.w = None
+        if g is None:
+            return d, None
+        lib = _lib.load()
+        B, V, Fin = d.shape
+        Fout = w.shape[0]
+        d = d.contiguous()
+        dx = torch.empty_like(d)
+        with torch.cuda.device(d.device):
+            ws = _workspace(lib.dsw_linear_workspace_bytes(B, V, Fin, Fout), d.device)
+            rc = lib.dsw_linear_bwd_acc(None, 0, 0, g.data_ptr(), w.data_ptr(), d.data_ptr(), dx.data_ptr(), None, None, B, V, Fin,
+                                        Fout, ws.data_ptr(), ws.numel(), _stream_ptr(d.device))
+        _lib.check(rc, "dsw_linear_bwd_acc")
+        return dx, None
+
+
+def fork(x):
+    """``(x_for_the_convolution_branch, state)``; hand ``state`` to ``linear_rezero(..., fork=state)``."""
+    state = _ForkState()
+    return ForkFunction.apply(x, state), state
+
+
 class LinearRezeroFunction(torch.autograd.Function):
     """The whole ResBlock tail when the skip connection is a Linear, in one launch:
     ``y = x @ W^T + b + rezero_weight * conv_out`` (``dsw_linear_rezero_fwd``: the channel-mix epilogue adds the
-    scaled convolution branch).  Backward = ``dsw_linear_bwd`` with ``dy = g`` and ``dsw_rezero_bwd``."""
+    scaled convolution branch).  Backward = ``dsw_linear_bwd`` with ``dy = g`` and ``dsw_rezero_bwd``.
+
+    ``cat_slot``: the output is written as the SECOND half of a fresh ``[B, V, 2 Fout]`` buffer (a strided view is
+    returned) so that the decoder's skip concatenation needs no copy (``unpool_cat``).  ``fork``: see ``ForkFunction``."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, conv_out, rezero_weight):
+    def forward(ctx, x, weight, bias, conv_out, rezero_weight, cat_slot=False, fork_state=None):
         for t, n in ((x, "x"), (weight, "weight"), (conv_out, "conv_out"), (rezero_weight, "rezero_weight")):
             _require_cuda_f32(t, n)
         B, V, Fin = x.shape
         Fout, Fin_w = weight.shape
         if Fin != Fin_w or tuple(conv_out.shape) != (B, V, Fout) or rezero_weight.numel() != 1:
             raise ValueError("shape mismatch in the fused residual tail")
+        _require_same_device(x, weight=weight, bias=bias, conv_out=conv_out, rezero_weight=rezero_weight)
         lib = _lib.load()
         x = x.contiguous()
         w = weight.contiguous()
         a = conv_out.contiguous()
         bptr = bias.contiguous().data_ptr() if bias is not None else None
-        y = torch.empty((B, V, Fout), dtype=torch.float32, device=x.device)
+        if cat_slot:
+            buf = torch.empty((B, V, 2 * Fout), dtype=torch.float32, device=x.device)
+            y = buf[:, :, Fout:]
+        else:
+            y = torch.empty((B, V, Fout), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             ws = _workspace(lib.dsw_linear_workspace_bytes(B, V, Fin, Fout), x.device)
-            rc = lib.dsw_linear_rezero_fwd(x.data_ptr(), x.stride(0), x.stride(1), w.data_ptr(), bptr, a.data_ptr(),
-                                           rezero_weight.data_ptr(), y.data_ptr(), B, V, Fin, Fout, ws.data_ptr(), ws.numel(),
-                                           _stream_ptr(x.device))
-        _lib.check(rc, "dsw_linear_rezero_fwd")
+            rc = lib.dsw_linear_rezero_fwd_ld(x.data_ptr(), x.stride(0), x.stride(1), w.data_ptr(), bptr, a.data_ptr(),
+                                              rezero_weight.data_ptr(), y.data_ptr(), y.stride(1), B, V, Fin, Fout, ws.data_ptr(),
+                                              ws.numel(), _stream_ptr(x.device))
+        _lib.check(rc, "dsw_linear_rezero_fwd_ld")
         ctx.save_for_backward(x, w, a, rezero_weight)
         ctx.has_bias = bias is not None
+        ctx.fork_state = fork_state
         return y
 
     @staticmethod
@@ -410,8 +468,11 @@ class LinearRezeroFunction(torch.autograd.Function):
         B, V, Fin = x.shape
         Fout = w.shape[0]
         g = g.contiguous()
-        need_dx, need_dw, need_db, need_a, need_rz = ctx.needs_input_grad
+        need_dx, need_dw, need_db, need_a, need_rz = ctx.needs_input_grad[:5]
         need_db = need_db and ctx.has_bias
+        if need_dx and ctx.fork_state is not None:  # the fork node adds the skip's share to the convolution branch's
+            ctx.fork_state.g, ctx.fork_state.w = g, w
+            need_dx = False
         dx = torch.empty_like(x) if need_dx else None
         dw = torch.empty_like(w) if need_dw else None
         db = torch.empty(Fout, dtype=torch.float32, device=x.device) if need_db else None
@@ -431,11 +492,11 @@ class LinearRezeroFunction(torch.autograd.Function):
                                         drz.data_ptr() if drz is not None else None, ws2.data_ptr(), ws2.numel(), a.numel(),
                                         _stream_ptr(x.device))
                 _lib.check(rc, "dsw_rezero_bwd")
-        return dx, dw, db, da, drz
+        return dx, dw, db, da, drz, None, None
 
 
-def linear_rezero(x, weight, bias, conv_out, rezero_weight):
-    return LinearRezeroFunction.apply(x, weight, bias, conv_out, rezero_weight)
+def linear_rezero(x, weight, bias, conv_out, rezero_weight, cat_slot=False, fork_state=None):
+    return LinearRezeroFunction.apply(x, weight, bias, conv_out, rezero_weight, cat_slot, fork_state)
 
 
 # --------------------------------------------------------------------------------------------
@@ -478,6 +539,114 @@ class RemapFunction(torch.autograd.Function):
 
 def remap(x, plan: SparsePlan):
     return RemapFunction.apply(x, plan)
+
+
+# --------------------------------------------------------------------------------------------
+# Skip concatenation without a concatenation pass        reference my_models_graph.py:505-538
+# --------------------------------------------------------------------------------------------
+
+
+def cat_slot_of(skip: torch.Tensor):
+    """The ``[B, V, 2C]`` buffer whose second half ``skip`` is (``LinearRezeroFunction(cat_slot=True)``), or None."""
+    if skip.dim() != 3 or not skip.is_cuda or skip.dtype != torch.float32:
+        return None
+    B, V, C = skip.shape
+    if skip.stride() != (V * 2 * C, 2 * C, 1) or skip.storage_offset() != C:
+        return None
+    if skip.untyped_storage().nbytes() < B * V * 2 * C * 4:
+        return None
+    return skip.as_strided((B, V, 2 * C), (V * 2 * C, 2 * C, 1), 0)
+
+
+class RemapCatFunction(torch.autograd.Function):
+    """``torch.cat((remap(x), skip), dim=2)`` (``x = self.unpool(x, idx); torch.cat((x, x_enc), dim=2)``,
+    ``my_models_graph.py:531-538``) where ``skip`` already occupies the second half of the result's buffer: the unpool
+    writes its rows into the first half (``dsw_spmm_fwd_ex``, strided output) and the buffer itself is returned."""
+
+    @staticmethod
+    def forward(ctx, x, plan: SparsePlan, skip):
+        _require_cuda_f32(x, "x")
+        buf = cat_slot_of(skip)
+        B, Vc, C = x.shape
+        if buf is None or skip.shape[2] != C or skip.shape[0] != B or skip.shape[1] != plan.shape[0]:
+            raise ValueError("skip is not the second half of a [B, V, 2C] concatenation buffer matching x")
+        if Vc != plan.shape[1]:
+            raise ValueError(f"x has {Vc} nodes but remap_matrix is {plan.shape}")
+        _require_same_device(x, remap_matrix=plan, skip=skip)
+        x = _channel_last(x)
+        with torch.cuda.device(x.device):
+            rc = _lib.load().dsw_spmm_fwd_ex(plan.handle, x.data_ptr(), x.stride(0), x.stride(1), None, 0, 0, buf.data_ptr(),
+                                             buf.stride(0), buf.stride(1), B, C, _stream_ptr(x.device))
+        _lib.check(rc, "dsw_spmm_fwd_ex")
+        ctx.plan = plan
+        ctx.C = C
+        return buf
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dcat):
+        plan, C = ctx.plan, ctx.C
+        dcat = _channel_last(dcat)
+        B = dcat.shape[0]
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((B, plan.shape[1], C), dtype=torch.float32, device=dcat.device)
+            with torch.cuda.device(dcat.device):
+                rc = _lib.load().dsw_spmm_bwd(plan.handle, dcat.data_ptr(), dcat.stride(0), dcat.stride(1), dx.data_ptr(), B, C,
+                                              _stream_ptr(dcat.device))
+            _lib.check(rc, "dsw_spmm_bwd")
+        return dx, None, (dcat[:, :, C:] if ctx.needs_input_grad[2] else None)
+
+
+class RemapForkFunction(torch.autograd.Function):
+    """``(remap(x), x)``: the encoder output feeds the pool and the decoder's skip connection
+    (``my_models_graph.py:505-511``).  One node owns both uses so that its backward adds the skip gradient inside the
+    transposed product (``dsw_spmm_bwd_ex``: dx = M^T d_pooled + d_skip) instead of in a separate element-wise pass."""
+
+    @staticmethod
+    def forward(ctx, x, plan: SparsePlan):
+        _require_cuda_f32(x, "x")
+        B, V, F = x.shape
+        if V != plan.shape[1]:
+            raise ValueError(f"x has {V} nodes but remap_matrix is {plan.shape}")
+        _require_same_device(x, remap_matrix=plan)
+        xs = _channel_last(x)
+        y = torch.empty((B, plan.shape[0], F), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.load().dsw_spmm_fwd(plan.handle, xs.data_ptr(), xs.stride(0), xs.stride(1), y.data_ptr(), B, F,
+                                          _stream_ptr(x.device))
+        _lib.check(rc, "dsw_spmm_fwd")
+        ctx.plan = plan
+        ctx.set_materialize_grads(False)
+        return y, x.as_strided(x.shape, x.stride(), x.storage_offset())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy, dskip):
+        plan = ctx.plan
+        if dy is None:
+            return dskip, None
+        dy = _channel_last(dy)
+        B, _, F = dy.shape
+        gp, gsb, gsv = None, 0, 0
+        if dskip is not None:
+            if dskip.stride(2) != 1 or (dskip.stride(0) | dskip.stride(1) | dskip.storage_offset()) % 4:
+                dskip = dskip.contiguous()
+            gp, gsb, gsv = dskip.data_ptr(), dskip.stride(0), dskip.stride(1)
+        dx = torch.empty((B, plan.shape[1], F), dtype=torch.float32, device=dy.device)
+        with torch.cuda.device(dy.device):
+            rc = _lib.load().dsw_spmm_bwd_ex(plan.handle, dy.data_ptr(), dy.stride(0), dy.stride(1), gp, gsb, gsv, dx.data_ptr(),
+                                             dx.stride(0), dx.stride(1), B, F, _stream_ptr(dy.device))
+        _lib.check(rc, "dsw_spmm_bwd_ex")
+        return dx, None
+
+
+def remap_cat(x, plan: SparsePlan, skip):
+    return RemapCatFunction.apply(x, plan, skip)
+
+
+def remap_fork(x, plan: SparsePlan):
+    return RemapForkFunction.apply(x, plan)
 
 
 # --------------------------------------------------------------------------------------------

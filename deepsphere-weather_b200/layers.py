@@ -164,12 +164,25 @@ class NodeLinear(torch.nn.Linear):
             return y[..., : self.out_features] if pout else y
         return super().forward(x)
 
-    def forward_rezero(self, x, conv_out, rezero_weight):
+    def fusable_rezero(self, x) -> bool:
+        """True when ``forward_rezero`` runs as the single fused launch on ``x`` itself (16-byte aligned channel counts)."""
+        return (x.dim() == 3 and x.is_cuda and x.dtype == torch.float32 and _pad4(self.in_features) == 0
+                and _pad4(self.out_features) == 0)
+
+    def forward_rezero(self, x, conv_out, rezero_weight, cat_slot=False, fork_state=None):
         """``self(x) + rezero_weight * conv_out`` — the ResBlock tail (``my_models_graph.py:211-215``) — in one
-        launch when the channel counts are 16-byte aligned, else the two-kernel composition."""
+        launch when the output channel count is 16-byte aligned (an unaligned input count is zero-padded first, which is
+        exact), else the two-kernel composition.  ``cat_slot`` / ``fork_state``: see ``functional.LinearRezeroFunction``
+        (only honoured by the fused launch; a fork needs aligned inputs)."""
         if (x.dim() == 3 and x.is_cuda and x.dtype == torch.float32 and conv_out.dtype == torch.float32
-                and _pad4(self.in_features) == 0 and _pad4(self.out_features) == 0):
-            return F_.linear_rezero(x, self.weight, self.bias, conv_out, rezero_weight)
+                and _pad4(self.out_features) == 0 and x.shape[2] == self.in_features):
+            pin = _pad4(self.in_features)
+            if pin == 0:
+                return F_.linear_rezero(x, self.weight, self.bias, conv_out, rezero_weight, cat_slot, fork_state)
+            if fork_state is None:
+                pad = torch.nn.functional.pad
+                return F_.linear_rezero(pad(x, (0, pin)), pad(self.weight, (0, pin)), self.bias, conv_out, rezero_weight,
+                                        cat_slot, None)
         return F_.rezero_residual(conv_out, self.forward(x), rezero_weight)
 
 
@@ -245,6 +258,27 @@ class RemapBlock(torch.nn.Module):
 
     def forward(self, x, *args, **kwargs):
         return F_.remap(x, F_.plan_for(self.remap_matrix))
+
+
+def pool_fork(pool, x):
+    """``(pooled, indices, skip)`` with ``skip`` the encoder output to hand to the decoder (``my_models_graph.py:505-511``:
+    ``x_enc = conv(x); x, idx = pool(x_enc)``).  For the sparse-remap pools one autograd node owns both uses, so the
+    backward adds the skip gradient inside the transposed product; other pools get the plain composition."""
+    if type(pool) in (GeneralAvgPool, GeneralMaxAreaPool) and x.is_cuda and x.dim() == 3 and x.dtype == torch.float32:
+        pooled, skip = F_.remap_fork(x, F_.plan_for(pool.remap_matrix))
+        return pooled, None, skip
+    pooled, idx = pool(x)
+    return pooled, idx, x
+
+
+def unpool_cat(unpool, x, idx, skip):
+    """``torch.cat((unpool(x, idx), skip), dim=2)`` (``my_models_graph.py:531-538``).  When ``skip`` was written into the
+    second half of a ``[B, V, 2C]`` buffer by its ResBlock (``cat_slot=True``) and the unpool is a sparse remap, the
+    unpool writes the first half in place and no concatenation pass runs."""
+    if (type(unpool) in (GeneralAvgUnpool, GeneralMaxAreaUnpool) and x.is_cuda and x.dim() == 3 and x.dtype == torch.float32
+            and x.shape[2] == skip.shape[2] and F_.cat_slot_of(skip) is not None):
+        return F_.remap_cat(x, F_.plan_for(unpool.remap_matrix), skip)
+    return torch.cat((unpool(x, idx), skip), dim=2)
 
 
 class GeneralAvgPool(RemapBlock):

@@ -26,6 +26,10 @@ from . import graphs as G
 
 # A/B switch (DSW_LINEAR_REZERO=0): two-kernel ResBlock tail instead of the fused Linear + ReZero launch
 _LINEAR_REZERO = os.environ.get("DSW_LINEAR_REZERO", "1") != "0"
+# A/B switch (DSW_FUSED_SKIPS=0): torch.cat for the skip concatenation and autograd's own gradient accumulation adds
+# instead of the cat-slot buffers / fork nodes
+_FUSED_SKIPS = os.environ.get("DSW_FUSED_SKIPS", "1") != "0"
+_FORK = os.environ.get("DSW_FORK", "1") != "0"  # A/B: fork nodes only
 
 
 def _default_backend():
@@ -38,6 +42,7 @@ def _default_backend():
         healpix_pools={"max": (L.HealpixMaxPool, L.HealpixMaxUnpool), "avg": (L.HealpixAvgPool, L.HealpixAvgUnpool)},
         general_pools=L.PoolUnpoolBlock.getGeneralPoolUnpoolLayer,
         rezero_residual=F_.rezero_residual,
+        fork=F_.fork, pool_fork=L.pool_fork, unpool_cat=L.unpool_cat,
     )
 
 
@@ -117,18 +122,33 @@ class ResBlock(torch.nn.Module):
         # fused `out * rezero_weight + skip` of the backend, if it has one
         backend = convblock_kwargs.get("backend") or _default_backend()
         self._fused_tail = getattr(backend, "rezero_residual", None)
+        self._fork = getattr(backend, "fork", None) if (_FUSED_SKIPS and _FORK) else None
         if convblock_kwargs.get("batch_norm", False):
             last = getattr(self, self.conv_names_list[-1])
             torch.nn.init.constant_(last.bn.weight, 0)
             torch.nn.init.constant_(last.bn.bias, 0)
 
-    def forward(self, x):
+    def forward(self, x, cat_slot=False):
+        """``cat_slot=True`` (an extension used by ``UNetSpherical.encode``): the output is written as the second half of
+        a ``[B, V, 2C]`` buffer, ready for the decoder's skip concatenation (``layers.unpool_cat``)."""
+        one_launch = (self.rezero and self._fused_tail is not None and _LINEAR_REZERO
+                      and hasattr(self.res_connection, "forward_rezero"))
+        if one_launch and self._fork is not None and self.res_connection.fusable_rezero(x):
+            # Linear skip + scale + add in one launch; the block's input gradient (convolution branch + skip) is finished
+            # by the fork node instead of an element-wise add
+            state = None
+            out = x
+            if torch.is_grad_enabled() and x.requires_grad:
+                out, state = self._fork(x)
+            for name in self.conv_names_list:
+                out = getattr(self, name)(out)
+            return self.res_connection.forward_rezero(x, out, self.rezero_weight, cat_slot=cat_slot, fork_state=state)
         out = x
         for name in self.conv_names_list:
             out = getattr(self, name)(out)
         if self.rezero and self._fused_tail is not None:
-            if _LINEAR_REZERO and hasattr(self.res_connection, "forward_rezero"):  # Linear skip + scale + add in one launch
-                return self.res_connection.forward_rezero(x, out, self.rezero_weight)
+            if one_launch:
+                return self.res_connection.forward_rezero(x, out, self.rezero_weight, cat_slot=cat_slot and _FUSED_SKIPS)
             return self._fused_tail(out, self.res_connection(x), self.rezero_weight)
         if self.rezero:
             out *= self.rezero_weight
@@ -251,6 +271,9 @@ class UNetSpherical(torch.nn.Module):
         else:
             raise ValueError("Not valid pooling method provided.")
 
+        fused_skips = _FUSED_SKIPS and conv_type == "graph" and skip_connection == "stack"
+        self._pool_fork = getattr(backend, "pool_fork", None) if fused_skips else None
+        self._unpool_cat = getattr(backend, "unpool_cat", None) if fused_skips else None
         L0, L1, L2 = self.laplacians
         self.conv1 = ResBlock(self.input_channels, (64, 128), laplacian=L0, convblock_kwargs=cb_kwargs)
         self.conv2 = ResBlock(128, (192, 256), laplacian=L1, convblock_kwargs=cb_kwargs)
@@ -267,6 +290,13 @@ class UNetSpherical(torch.nn.Module):
         x_last = x[:, -1, :, -2:].unsqueeze(dim=1)
         x = x.rename(*self.dim_names).align_to("sample", "node", "time", "feature").rename(None)
         x = x.reshape(batch, self.input_n_node, self.input_channels)
+        if self._pool_fork is not None:  # skip tensors land in their concatenation buffers; pool + skip share one node
+            enc1 = self.conv1(x, cat_slot=True)
+            pooled1, idx1, enc1 = self._pool_fork(self.pool1, enc1)
+            enc2 = self.conv2(pooled1, cat_slot=True)
+            pooled2, idx2, enc2 = self._pool_fork(self.pool2, enc2)
+            enc3 = self.conv3(pooled2)
+            return enc3, enc2, enc1, idx2, idx1, x_last
         enc1 = self.conv1(x)
         pooled1, idx1 = self.pool1(enc1)
         enc2 = self.conv2(pooled1)
@@ -276,10 +306,14 @@ class UNetSpherical(torch.nn.Module):
 
     # reference: my_models_graph.py:528-564
     def decode(self, enc3, enc2, enc1, idx2, idx1, x_last):
-        x = self.unpool2(enc3, idx2)
-        x = self.uconv2(torch.cat((x, enc2), dim=2))
-        x = self.unpool1(x, idx1)
-        x = self.uconv1(torch.cat((x, enc1), dim=2))
+        if self._unpool_cat is not None:
+            x = self.uconv2(self._unpool_cat(self.unpool2, enc3, idx2, enc2))
+            x = self.uconv1(self._unpool_cat(self.unpool1, x, idx1, enc1))
+        else:
+            x = self.unpool2(enc3, idx2)
+            x = self.uconv2(torch.cat((x, enc2), dim=2))
+            x = self.unpool1(x, idx1)
+            x = self.uconv1(torch.cat((x, enc1), dim=2))
         x = self.uconv1_final(x)
         batch = x.shape[0]
         x = x.reshape(batch, self.output_n_node, self.output_n_time, self.output_n_feature)

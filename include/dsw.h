@@ -140,6 +140,12 @@ int dsw_linear_fwd(const float* x, int64_t x_sB, int64_t x_sV, const float* Wl, 
 int dsw_linear_bwd(const float* x, int64_t x_sB, int64_t x_sV, const float* dy, const float* Wl,
                    float* dx, float* dW, float* dbias, int32_t B, int32_t V, int32_t Fin, int32_t Fout,
                    void* workspace, size_t workspace_bytes, void* stream);
+/* Same with the input gradient accumulated:  dx = dy . Wl + dx_addend  (dx_addend [B][V][Fin] contiguous or NULL).
+ * A ResBlock's input receives two gradients — the convolution branch's and the skip connection's
+ * (my_models_graph.py:205-215; torch adds them in a separate pass): the skip's backward adds the other in its epilogue. */
+int dsw_linear_bwd_acc(const float* x, int64_t x_sB, int64_t x_sV, const float* dy, const float* Wl, const float* dx_addend,
+                       float* dx, float* dW, float* dbias, int32_t B, int32_t V, int32_t Fin, int32_t Fout, void* workspace,
+                       size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Sparse remap (interpolation pooling / unpooling).  Replaces RemapBlock.forward
@@ -151,6 +157,15 @@ int dsw_spmm_fwd(const dsw_plan* mat, const float* x, int64_t x_sB, int64_t x_sV
                  int32_t B, int32_t F, void* stream);
 int dsw_spmm_bwd(const dsw_plan* mat, const float* dy, int64_t dy_sB, int64_t dy_sV, float* dx,
                  int32_t B, int32_t F, void* stream);
+/* The same two products with an optional addend (indexed like the output rows, element strides a_sB / a_sV, or NULL) and
+ * a strided output (row stride >= F):  y = M x + addend,  dx = M^T dy + addend.  They carry the U-Net's skip connection
+ * (my_models_graph.py:533,538 `torch.cat((x, x_enc), dim=2)`) without a concatenation pass: the unpool writes its rows
+ * straight into one half of the [B][V][2C] tensor the decoder reads (the encoder's last kernel wrote the other half), and
+ * the pool's backward adds the skip half of the decoder's input gradient to its own result. */
+int dsw_spmm_fwd_ex(const dsw_plan* mat, const float* x, int64_t x_sB, int64_t x_sV, const float* addend, int64_t a_sB,
+                    int64_t a_sV, float* y, int64_t y_sB, int64_t y_sV, int32_t B, int32_t F, void* stream);
+int dsw_spmm_bwd_ex(const dsw_plan* mat, const float* dy, int64_t dy_sB, int64_t dy_sV, const float* addend, int64_t a_sB,
+                    int64_t a_sV, float* dx, int64_t dx_sB, int64_t dx_sV, int32_t B, int32_t F, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Max-value pooling with index output.  Replaces GeneralMaxValPool.forward
@@ -211,6 +226,11 @@ int dsw_nested_sum(const float* x, int64_t x_sB, int64_t x_sV, float* y, int32_t
 int dsw_linear_rezero_fwd(const float* x, int64_t x_sB, int64_t x_sV, const float* Wl, const float* bias, const float* conv_out,
                           const float* scale, float* y, int32_t B, int32_t V, int32_t Fin, int32_t Fout, void* workspace,
                           size_t workspace_bytes, void* stream);
+/* Same, y written with row stride y_ld >= Fout (row n = b*V + v at y + n*y_ld): the encoder's output lands in its half of
+ * the skip-concatenation buffer (see dsw_spmm_fwd_ex). */
+int dsw_linear_rezero_fwd_ld(const float* x, int64_t x_sB, int64_t x_sV, const float* Wl, const float* bias, const float* conv_out,
+                             const float* scale, float* y, int64_t y_ld, int32_t B, int32_t V, int32_t Fin, int32_t Fout,
+                             void* workspace, size_t workspace_bytes, void* stream);
 int dsw_rezero_fwd(const float* conv_out, const float* skip, const float* w, float* y, int64_t n, void* stream);
 size_t dsw_rezero_bwd_workspace_bytes(void);
 int dsw_rezero_bwd(const float* g, const float* conv_out, const float* w, float* d_conv_out, float* d_w, void* workspace,
@@ -248,7 +268,7 @@ enum {
   DSW_OPT_L2_CHUNK_BYTES = 1, /* working-set budget (bytes) of L2-resident sample chunks; 0 / 1 = chunking off (default) */
   DSW_OPT_DEBUG = 2,          /* timing experiments only (results become wrong): 1 = hops skip staging, 2 = hops skip the FMA loop;
                                  dense kernels, bit mask: 16 = no output stores, 32 = no A transfers, 64 = no B transfers,
-                                 128 = no bf16 conversion, 256 = no MMAs */
+                                 128 = no bf16 conversion, 256 = no MMAs; 1024 = A/B (results stay right): no L2 prefetch of the mix epilogue's addend */
   DSW_OPT_NO_TMA = 3,         /* 1 = stage tiles with cp.async / register loads instead of tensor-map TMA */
   DSW_OPT_FWD_ALGO = 4,       /* 0 = auto by channel counts, 1 = TERMS (hops on Fin, then mix), 2 = CLENSHAW (mix, then hops on Fout) */
   DSW_OPT_BWD_ALGO = 5,       /* 0 = auto, 1 = TERMS (hops on dy, Fout channels), 2 = CLENSHAW (hops on Fin channels) */

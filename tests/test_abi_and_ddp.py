@@ -59,6 +59,11 @@ def test_new_entry_points_validate_arguments_without_a_gpu(lib):
     assert lib.dsw_rezero_bwd(None, None, None, None, None, None, 0, 16, None) < 0
     assert lib.dsw_linear_rezero_fwd(None, 0, 0, None, None, None, None, None, 1, 1, 4, 4, None, 0, None) < 0
     assert lib.dsw_debug_dense_counters(None, 0) < 0
+    # strided / accumulating forms of the skip-connection path
+    assert lib.dsw_linear_rezero_fwd_ld(None, 0, 0, None, None, None, None, None, 8, 1, 1, 4, 4, None, 0, None) < 0
+    assert lib.dsw_linear_bwd_acc(None, 0, 0, None, None, None, None, None, None, 1, 1, 4, 4, None, 0, None) < 0
+    assert lib.dsw_spmm_fwd_ex(None, None, 0, 0, None, 0, 0, None, 0, 0, 1, 4, None) < 0
+    assert lib.dsw_spmm_bwd_ex(None, None, 0, 0, None, 0, 0, None, 0, 0, 1, 4, None) < 0
 
 
 def test_tuning_options_round_trip_and_env_hook(lib):

@@ -977,3 +977,112 @@ def test_weighted_mse_label_gradient_and_device_checks(dev):
     assert torch.equal(l.grad, -p.grad) and float(p.grad.abs().max()) > 0
     with pytest.raises(RuntimeError, match="CUDA|device"):
         F_.cheb_terms(torch.randn(1, 48, 4), F_.plan_for(G.healpix_laplacian(2).to(dev)), 3)
+
+
+# ----------------------------------------------------------------------------------------------
+# Skip connections without concatenation / accumulation passes
+# ----------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("B,nside,C", [(2, 8, 64), (3, 4, 32), (1, 8, 128)])
+def test_remap_cat_and_fork_match_torch_composition(B, nside, C, dev, mix_mode):
+    """`torch.cat((unpool(x), skip), dim=2)` and `(pool(enc), enc)` (my_models_graph.py:505-538) through the strided /
+    accumulating remap entry points against the plain composition in torch on the CPU, values and gradients."""
+    from deepsphere_weather_b200 import functional as F_
+    from deepsphere_weather_b200 import graphs as G
+    from deepsphere_weather_b200 import layers as L
+
+    torch.manual_seed(21)
+    V = 12 * nside * nside
+    pool_m, unpool_m = G.nested_pool_matrices(V, 4)
+    pool, unpool = L.PoolUnpoolBlock.getGeneralPoolUnpoolLayer(pool_method="interp", matrices=(pool_m, unpool_m))
+    P, U = pool.remap_matrix.to_dense(), unpool.remap_matrix.to_dense()
+    lin = L.NodeLinear(24, C)
+    xin, conv_out, coarse = torch.randn(B, V, 24), torch.randn(B, V, C), torch.randn(B, V // 4, C)
+    rz = torch.full((1,), 0.6)
+    gcat, gpool = torch.randn(B, V, 2 * C), torch.randn(B, V // 4, C)
+
+    # reference composition (CPU)
+    xr, ar, cr = (t.clone().requires_grad_(True) for t in (xin, conv_out, coarse))
+    enc = ar * rz + torch.nn.functional.linear(xr, lin.weight, lin.bias)
+    pooled = torch.einsum("cv,bvf->bcf", P, enc)
+    cat = torch.cat((torch.einsum("vc,bcf->bvf", U, cr), enc), dim=2)
+    (cat * gcat).sum().backward(retain_graph=True)
+    (pooled * gpool).sum().backward()
+    ref = [xr.grad, ar.grad, cr.grad, lin.weight.grad.clone(), lin.bias.grad.clone()]
+    lin.zero_grad(set_to_none=True)
+
+    lin, pool, unpool = lin.to(dev), pool.to(dev), unpool.to(dev)
+    xd, ad, cd = (t.to(dev).requires_grad_(True) for t in (xin, conv_out, coarse))
+    encd = lin.forward_rezero(xd, ad, rz.to(dev), cat_slot=True)
+    assert F_.cat_slot_of(encd) is not None and not encd.is_contiguous()
+    pooled_d, idx, skip = L.pool_fork(pool, encd)
+    assert idx is None
+    catd = L.unpool_cat(unpool, cd, None, skip)
+    assert catd.is_contiguous() and catd.data_ptr() == F_.cat_slot_of(encd).data_ptr()  # no copy was made
+    assert rel_err(pooled_d, pooled) < REL_TOL and rel_err(catd, cat) < REL_TOL
+    ((catd * gcat.to(dev)).sum() + (pooled_d * gpool.to(dev)).sum()).backward()
+    for got, want in zip([xd.grad, ad.grad, cd.grad, lin.weight.grad, lin.bias.grad], ref):
+        assert rel_err(got, want) < REL_TOL
+    # a skip that is NOT in a concatenation slot takes the plain composition
+    dense_skip = encd.detach().contiguous()
+    assert rel_err(L.unpool_cat(unpool, cd.detach(), None, dense_skip), cat) < REL_TOL
+
+
+@pytest.mark.parametrize("B,V,Fin,Fout", [(2, 768, 64, 128), (1, 500, 256, 64)])
+def test_fork_adds_the_skip_gradient_in_the_mix_epilogue(B, V, Fin, Fout, dev, mix_mode):
+    """A ResBlock input feeds the convolution branch and the Linear skip (my_models_graph.py:205-215); with a fork node
+    the input gradient g.Wl + d_conv comes out of one kernel (dsw_linear_bwd_acc) and equals autograd's two-pass sum."""
+    from deepsphere_weather_b200 import functional as F_
+    from deepsphere_weather_b200 import layers as L
+
+    torch.manual_seed(5)
+    lin = L.NodeLinear(Fin, Fout)
+    mixw = torch.randn(Fin, Fout) / Fin**0.5
+    x, g = torch.randn(B, V, Fin), torch.randn(B, V, Fout)
+    rz = torch.full((1,), 0.9)
+    xr = x.clone().requires_grad_(True)
+    out = (torch.tanh(xr) @ mixw) * rz + torch.nn.functional.linear(xr, lin.weight, lin.bias)
+    out.backward(g)
+    ref = [xr.grad, lin.weight.grad.clone(), lin.bias.grad.clone()]
+    lin.zero_grad(set_to_none=True)
+    lin = lin.to(dev)
+    xd = x.to(dev).requires_grad_(True)
+    xc, state = F_.fork(xd)
+    conv_out = torch.tanh(xc) @ mixw.to(dev)  # stand-in for the convolution branch
+    y = lin.forward_rezero(xd, conv_out, rz.to(dev), fork_state=state)
+    y.backward(g.to(dev))
+    assert state.g is None  # consumed by the fork node
+    assert rel_err(y, out.detach()) < REL_TOL
+    for got, want in zip([xd.grad, lin.weight.grad, lin.bias.grad], ref):
+        assert rel_err(got, want) < REL_TOL
+
+
+def test_unet_fused_skips_match_plain_composition(dev, lib):
+    """The whole U-Net with cat-slot buffers + fork nodes (default) against the same net with torch.cat and autograd's own
+    accumulation (DSW_FUSED_SKIPS=0): outputs, input gradient and every parameter gradient."""
+    from deepsphere_weather_b200 import graphs as G
+    from deepsphere_weather_b200 import models as M
+
+    laps = [G.healpix_laplacian(n) for n in (8, 4, 2)]
+    x = torch.randn(2, 3, 768, 7, generator=torch.Generator().manual_seed(3))
+    results = []
+    for fused in (True, False):
+        old = M._FUSED_SKIPS
+        M._FUSED_SKIPS = fused
+        try:
+            net = M.UNetSpherical(M.default_tensor_info(768), "healpix", {"subdivisions": 8, "nest": True},
+                                  kernel_size_conv=4, pool_method="interp", laplacians=laps)
+        finally:
+            M._FUSED_SKIPS = old
+        M.deterministic_fill(net, 1, rezero=0.7)
+        net = net.to(dev)
+        xd = x.to(dev).requires_grad_(True)
+        n0 = lib.dsw_launch_count()
+        y = net(xd)
+        y.square().mean().backward()
+        results.append((y.detach(), xd.grad, {n: p.grad for n, p in net.named_parameters()}, lib.dsw_launch_count() - n0))
+    (yf, dxf, gf, _), (yp, dxp, gp, _) = results
+    assert rel_err(yf, yp) < 1e-5 and rel_err(dxf, dxp) < 1e-5
+    for n in gp:
+        assert rel_err(gf[n], gp[n]) < 1e-5, n
