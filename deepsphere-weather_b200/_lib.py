@@ -35,6 +35,7 @@ SIGNATURES = {
     "dsw_cheb_bwd_algo": (C.c_int, [_i32] * 3),
     "dsw_cheb_bwd_workspace_bytes": (_sz, [_i32] * 6),
     "dsw_cheb_bwd": (C.c_int, [_ptr, _ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _sz, _ptr]),
+    "dsw_cheb_bwd_ex": (C.c_int, [_ptr, _ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _i32, _ptr, _sz, _ptr]),
     "dsw_cheb_bwd_data_workspace_bytes": (_sz, [_i32] * 5),
     "dsw_cheb_bwd_data": (C.c_int, [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _sz, _ptr]),
     "dsw_cheb_bwd_weight_workspace_bytes": (_sz, [_i32] * 5),

@@ -509,6 +509,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
             if (ch[j] >= slab_f) continue;
             float4 o = make_float4(H.alpha * acc[r][j].x, H.alpha * acc[r][j].y, H.alpha * acc[r][j].z, H.alpha * acc[r][j].w);
             if (H.act) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+            if (H.M != nullptr) {  // ReLU mask of a gradient by the ReLU's output (indexed like the output rows)
+              const float4 m = ldcg4(H.M + d.b * H.m_sB + (int64_t)row * H.m_sV + d.slab * 64 + ch[j]);
+              o.x = m.x > 0.f ? o.x : 0.f, o.y = m.y > 0.f ? o.y : 0.f, o.z = m.z > 0.f ? o.z : 0.f, o.w = m.w > 0.f ? o.w : 0.f;
+            }
             *reinterpret_cast<float4*>(H.O + d.b * H.o_sB + (int64_t)row * H.o_sV + d.slab * 64 + ch[j]) = o;
           }
         }
@@ -572,6 +576,7 @@ static bool chain_ok(const dsw_csr& A, const dsw_rb& rb, const ChainHop* h, int 
     if (!c.X || !c.O || !aligned16(c.X) || !aligned16(c.O) || (c.x_sB | c.x_sV | c.o_sB | c.o_sV) % 4 || c.x_sV < F) return false;
     if (c.Z && (!aligned16(c.Z) || (c.z_sB | c.z_sV) % 4)) return false;
     if (c.G && (!aligned16(c.G) || (c.g_sB | c.g_sV) % 4)) return false;
+    if (c.M && (!aligned16(c.M) || (c.m_sB | c.m_sV) % 4)) return false;
     if (!(c.alpha == 1.f || c.alpha == 2.f)) return false;
     // hop j gathers from hop j-1's output
     if (j > 0 && (c.X != h[j - 1].O || c.x_sB != h[j - 1].o_sB || c.x_sV != h[j - 1].o_sV)) return false;
@@ -627,6 +632,7 @@ static int launch_chain_fused(const dsw_csr& A, const dsw_rb& rb, const ChainHop
     c.X += B0 * c.x_sB, c.O += B0 * c.o_sB;
     if (c.Z) c.Z += B0 * c.z_sB;
     if (c.G) c.G += B0 * c.g_sB;
+    if (c.M) c.M += B0 * c.m_sB;
     c.dep = j > 0 ? 1 : 0;
     args.h[j] = c;
     const uint64_t dims[3] = {(uint64_t)F, (uint64_t)A.n_cols, (uint64_t)Bn};
@@ -674,6 +680,7 @@ int launch_hop_chain(const dsw_csr& A, const dsw_rb& rb, const ChainHop* hops, i
     a.G = c.G, a.g_sB = c.g_sB, a.g_sV = c.g_sV;
     a.O = c.O, a.o_sB = c.o_sB, a.o_sV = c.o_sV;
     a.alpha = c.alpha, a.beta = c.beta, a.B = B, a.F = F, a.act = c.act;
+    a.M = c.M, a.m_sB = c.m_sB, a.m_sV = c.m_sV;
     DSW_TRY(launch_hop(A, rb, a, st));
   }
   return DSW_OK;

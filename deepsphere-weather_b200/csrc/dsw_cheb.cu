@@ -113,7 +113,8 @@ static int run_terms(const dsw_csr& A, const dsw_rb& rb, const float* x, int64_t
 // Clenshaw recurrence under operator A, in place on the K planes G ([K][plane], F channels):
 //   b_{K-1} = G_{K-1};  b_k = G_k + 2 A b_{k+1} - b_{k+2}  (k = K-2 .. 1);  out = G_0 + A b_1 - b_2
 static int run_clenshaw(const dsw_csr& A, const dsw_rb& rb, float* G, int64_t plane, float* out, int32_t Bc, int32_t F,
-                        int32_t K, cudaStream_t st, int32_t act = 0) {
+                        int32_t K, cudaStream_t st, int32_t act = 0, const float* mask = nullptr, int64_t m_sB = 0,
+                        int64_t m_sV = 0) {
   const int64_t V = A.n_rows, sB = V * F, sV = F;
   ChainHop hops[DSW_MAX_K];
   int n = 0;
@@ -125,6 +126,7 @@ static int run_clenshaw(const dsw_csr& A, const dsw_rb& rb, float* G, int64_t pl
     a.alpha = (k == 0) ? 1.f : 2.f;
     a.O = (k == 0) ? out : G + k * plane, a.o_sB = sB, a.o_sV = sV;
     a.act = (k == 0) ? act : 0;  // the activation follows the last hop
+    if (k == 0 && mask) a.M = mask, a.m_sB = m_sB, a.m_sV = m_sV;  // so does the ReLU mask of an input gradient
   }
   return launch_hop_chain(A, rb, hops, n, Bc, F, st);
 }
@@ -274,9 +276,21 @@ size_t dsw_cheb_bwd_workspace_bytes(int32_t B, int32_t V, int32_t Fin, int32_t F
 int dsw_cheb_bwd(const dsw_plan* lap, const float* x, int64_t x_sB, int64_t x_sV, const float* dy, const float* W,
                  const float* saved_terms, float* dx, float* dW, float* dbias, int32_t B, int32_t Fin, int32_t Fout,
                  int32_t K, void* workspace, size_t workspace_bytes, void* stream) {
+  return dsw_cheb_bwd_ex(lap, x, x_sB, x_sV, dy, W, saved_terms, dx, dW, dbias, B, Fin, Fout, K, 0, workspace, workspace_bytes,
+                         stream);
+}
+
+int dsw_cheb_bwd_ex(const dsw_plan* lap, const float* x, int64_t x_sB, int64_t x_sV, const float* dy, const float* W,
+                    const float* saved_terms, float* dx, float* dW, float* dbias, int32_t B, int32_t Fin, int32_t Fout,
+                    int32_t K, int32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
   DSW_TRY(check_common(lap, B, Fin, Fout, K));
-  if (!dy || (!dx && !dW) || (dx && !W) || (dW && !x)) return DSW_ERR_BAD_ARGUMENT;
+  if (!dy || (!dx && !dW) || (dx && !W) || (dW && !x) || (flags & ~DSW_BWD_MASK_DX_BY_X)) return DSW_ERR_BAD_ARGUMENT;
+  // x = relu(.) upstream: its gradient is dx * [x > 0]; applied where the last kernel writes dx
+  const bool mask_dx = (flags & DSW_BWD_MASK_DX_BY_X) && dx;
+  if (mask_dx && !x) return DSW_ERR_BAD_ARGUMENT;
   const int32_t V = lap->fwd.n_rows;
+  // the channel mix indexes its epilogue operand by the flat row n = b * V + v
+  if (mask_dx && B > 1 && x_sB != (int64_t)V * x_sV) return DSW_ERR_UNSUPPORTED;
   const bool need_xterms = dW != nullptr && saved_terms == nullptr;
   const BwdLayout L = bwd_layout(B, V, Fin, Fout, K, need_xterms);
   if (!workspace || workspace_bytes < dsw_cheb_bwd_workspace_bytes(B, V, Fin, Fout, K, need_xterms ? 0 : 1))
@@ -310,8 +324,10 @@ int dsw_cheb_bwd(const dsw_plan* lap, const float* x, int64_t x_sB, int64_t x_sV
         m.A[0] = dyc, m.a_sB[0] = (int64_t)V * Fout, m.a_sV[0] = Fout;
         m.Bm = W, m.sBp = 0, m.sBk = 1, m.sBc0 = (int64_t)K * Fout, m.sBc1 = Fout;
         m.bias = nullptr, m.C = G, m.sCp = plane, m.ldc = Fin, m.Cw = Fin, m.Nc = K * Fin, m.act = 0;
+        if (mask_dx && K == 1) m.R = xc, m.ldr = x_sV, m.r_mode = 1;
         DSW_TRY(launch_mix(m, prep, L.prep_bytes, c == 0, st));
-        if (K > 1) DSW_TRY(run_clenshaw(lap->tr, lap->tr_rb, G, plane, dxc, Bc, Fin, K, st));
+        if (K > 1)
+          DSW_TRY(run_clenshaw(lap->tr, lap->tr_rb, G, plane, dxc, Bc, Fin, K, st, 0, mask_dx ? xc : nullptr, x_sB, x_sV));
       }
       if (dW) {
         const int64_t plane = (int64_t)Bc * V * Fin;
@@ -339,6 +355,7 @@ int dsw_cheb_bwd(const dsw_plan* lap, const float* x, int64_t x_sB, int64_t x_sV
         for (int k = 1; k < K; ++k) m.A[k] = U + (k - 1) * plane, m.a_sB[k] = (int64_t)V * Fout, m.a_sV[k] = Fout;
         m.Bm = W, m.sBp = Fout, m.sBk = 1, m.sBc0 = (int64_t)K * Fout, m.sBc1 = 0;
         m.bias = nullptr, m.C = dxc, m.sCp = 0, m.ldc = Fin, m.Cw = Fin, m.Nc = Fin, m.act = 0;
+        if (mask_dx) m.R = xc, m.ldr = x_sV, m.r_mode = 1;
         DSW_TRY(launch_mix(m, prep, L.prep_bytes, c == 0, st));
       }
       if (dW) {

@@ -158,6 +158,8 @@ struct HopArgs {
   float alpha = 1.f, beta = 0.f;
   int32_t B = 0, F = 0;
   int32_t act = 0;           // 1 = ReLU on the result (the last hop of a fused conv + activation)
+  const float* M = nullptr;  // optional mask, indexed like the output rows: O = (M > 0) ? O : 0
+  int64_t m_sB = 0, m_sV = 0;
 };
 int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_t st);
 
@@ -174,6 +176,8 @@ struct ChainHop {
   float alpha = 1.f, beta = 0.f;
   int32_t act = 0;
   int32_t dep = 0;  // set by the launcher: 1 = wait for the previous hop's tiles
+  const float* M = nullptr;  // optional mask (see HopArgs)
+  int64_t m_sB = 0, m_sV = 0;
 };
 int launch_hop_chain(const dsw_csr& A, const dsw_rb& rb, const ChainHop* hops, int n, int32_t B, int32_t F, cudaStream_t st);
 
@@ -201,6 +205,7 @@ struct MixArgs {
   const float* R = nullptr;
   int64_t ldr = 0;
   const float* r_scale = nullptr;  // device scalar; null = 1
+  int32_t r_mode = 0;              // 0: C += r_scale * R;  1: C = (R > 0) ? C : 0  (ReLU mask of a gradient by the ReLU's output)
 };
 int launch_mix_simt(const MixArgs& a, cudaStream_t st);
 

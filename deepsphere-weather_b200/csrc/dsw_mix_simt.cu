@@ -113,7 +113,10 @@ __global__ void __launch_bounds__(256) mix_simt_kernel(MixArgs a) {
       const int64_t n = n0 + ty * TM + i;
       if (n >= a.N) continue;
       float v = acc[i][j] + bz;
-      if (a.R) v = fmaf(a.r_scale ? __ldg(a.r_scale) : 1.f, __ldg(a.R + n * a.ldr + cg), v);
+      if (a.R) {
+        const float rr = __ldg(a.R + n * a.ldr + cg);
+        v = a.r_mode == 1 ? (rr > 0.f ? v : 0.f) : fmaf(a.r_scale ? __ldg(a.r_scale) : 1.f, rr, v);
+      }
       if (a.act == 1) v = fmaxf(v, 0.f);
       Cb[n * a.ldc] = v;
     }

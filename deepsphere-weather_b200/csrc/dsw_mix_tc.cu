@@ -424,7 +424,10 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tc_kernel(const __grid_consta
           for (int e = 0; e < 4; ++e) {
             v[e] = __uint_as_float(r[j + e]);
             if (a.bias && cg + e < a.bias_n) v[e] += __ldg(a.bias + cg + e);
-            if (a.R && cg + e < a.Nc) v[e] = fmaf(a.r_scale ? __ldg(a.r_scale) : 1.f, __ldg(a.R + n * a.ldr + cg + e), v[e]);
+            if (a.R && cg + e < a.Nc) {
+              const float rr = __ldg(a.R + n * a.ldr + cg + e);
+              v[e] = a.r_mode == 1 ? (rr > 0.f ? v[e] : 0.f) : fmaf(a.r_scale ? __ldg(a.r_scale) : 1.f, rr, v[e]);
+            }
             if (a.act == 1) v[e] = fmaxf(v[e], 0.f);
           }
           if (vec_store && cg + 3 < a.Nc) {
@@ -712,6 +715,7 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
           if (ADDEND && addend_vec) {
             // same, plus the addend row segments (C += r_scale * R)
             const float rs = a.r_scale ? __ldg(a.r_scale) : 1.f;
+            const bool mask_mode = a.r_mode == 1;
             float* cp_row = cbase + (row0 + half) * a.ldc;
             const int64_t step = 2 * (int64_t)a.ldc;
             int64_t n = row0 + half;
@@ -730,8 +734,13 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
                 if (n >= a.N) continue;
                 float4 o = v[i];
                 const float4 r4 = rv[i0 + i];
-                o.x = fmaf(rs, r4.x, o.x + bv[0]), o.y = fmaf(rs, r4.y, o.y + bv[1]);
-                o.z = fmaf(rs, r4.z, o.z + bv[2]), o.w = fmaf(rs, r4.w, o.w + bv[3]);
+                if (mask_mode) {  // ReLU mask of a gradient by the ReLU's output
+                  o.x = r4.x > 0.f ? o.x + bv[0] : 0.f, o.y = r4.y > 0.f ? o.y + bv[1] : 0.f;
+                  o.z = r4.z > 0.f ? o.z + bv[2] : 0.f, o.w = r4.w > 0.f ? o.w + bv[3] : 0.f;
+                } else {
+                  o.x = fmaf(rs, r4.x, o.x + bv[0]), o.y = fmaf(rs, r4.y, o.y + bv[1]);
+                  o.z = fmaf(rs, r4.z, o.z + bv[2]), o.w = fmaf(rs, r4.w, o.w + bv[3]);
+                }
                 if (relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
                 *reinterpret_cast<float4*>(cp_row) = o;
               }
@@ -765,7 +774,10 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 if (col + e >= a.Nc) break;
-                if (ADDEND && a.R) ve[e] = fmaf(a.r_scale ? __ldg(a.r_scale) : 1.f, __ldg(a.R + n * a.ldr + col + e), ve[e]);
+                if (ADDEND && a.R) {
+                  const float rr = __ldg(a.R + n * a.ldr + col + e);
+                  ve[e] = a.r_mode == 1 ? (rr > 0.f ? ve[e] : 0.f) : fmaf(a.r_scale ? __ldg(a.r_scale) : 1.f, rr, ve[e]);
+                }
                 const int cpe = (col + e) / a.Cw, cce = (col + e) - cpe * a.Cw;
                 a.C[(int64_t)cpe * a.sCp + n * a.ldc + cce] = relu ? fmaxf(ve[e], 0.f) : ve[e];
               }

@@ -98,6 +98,10 @@ __global__ void __launch_bounds__(512) hop_rb_kernel(const int32_t* __restrict__
       o.x += g.x, o.y += g.y, o.z += g.z, o.w += g.w;
     }
     if (a.act) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+    if (a.M) {  // ReLU mask of a gradient by the ReLU's output (indexed like the output rows)
+      const float4 m = ldg4(a.M + b * a.m_sB + row * a.m_sV + c4 * 4);
+      o.x = m.x > 0.f ? o.x : 0.f, o.y = m.y > 0.f ? o.y : 0.f, o.z = m.z > 0.f ? o.z : 0.f, o.w = m.w > 0.f ? o.w : 0.f;
+    }
     *reinterpret_cast<float4*>(a.O + b * a.o_sB + row * a.o_sV + c4 * 4) = o;
   }
 }
@@ -156,7 +160,9 @@ __global__ void __launch_bounds__(256) hop_csr_kernel(const int32_t* __restrict_
       float o = a.alpha * acc[i];
       if (a.Z) o = fmaf(a.beta, __ldg(a.Z + b * a.z_sB + row * a.z_sV + f + i), o);
       if (a.G) o += __ldg(a.G + b * a.g_sB + row * a.g_sV + f + i);
-      acc[i] = a.act ? fmaxf(o, 0.f) : o;
+      if (a.act) o = fmaxf(o, 0.f);
+      if (a.M) o = __ldg(a.M + b * a.m_sB + row * a.m_sV + f + i) > 0.f ? o : 0.f;
+      acc[i] = o;
     }
     float* op = a.O + b * a.o_sB + row * a.o_sV + f;
     if constexpr (VEC == 4) {
@@ -281,6 +287,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 3) hop_tile_kernel(const int32_t
           o.x += g.x, o.y += g.y, o.z += g.z, o.w += g.w;
         }
         if (a.act) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+        if (a.M) {  // ReLU mask of a gradient by the ReLU's output (indexed like the output rows)
+          const float4 m = ldg4(a.M + b * a.m_sB + row * a.m_sV + col);
+          o.x = m.x > 0.f ? o.x : 0.f, o.y = m.y > 0.f ? o.y : 0.f, o.z = m.z > 0.f ? o.z : 0.f, o.w = m.w > 0.f ? o.w : 0.f;
+        }
         *reinterpret_cast<float4*>(a.O + b * a.o_sB + row * a.o_sV + col) = o;
       }
     }
@@ -692,6 +702,10 @@ __global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
           const int64_t col = (int64_t)slab * 64 + ch[j];
           float4 o = make_float4(a.alpha * acc[r][j].x, a.alpha * acc[r][j].y, a.alpha * acc[r][j].z, a.alpha * acc[r][j].w);
           if (a.act) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+          if (a.M) {  // ReLU mask of a gradient by the ReLU's output (indexed like the output rows)
+            const float4 m = ldg4(a.M + b * a.m_sB + row * a.m_sV + col);
+            o.x = m.x > 0.f ? o.x : 0.f, o.y = m.y > 0.f ? o.y : 0.f, o.z = m.z > 0.f ? o.z : 0.f, o.w = m.w > 0.f ? o.w : 0.f;
+          }
           *reinterpret_cast<float4*>(a.O + b * a.o_sB + row * a.o_sV + col) = o;
         }
       }
@@ -727,6 +741,7 @@ static bool vec4_ok(const HopArgs& a) {
   if (!aligned16(a.X) || !aligned16(a.O) || (a.x_sB | a.x_sV | a.o_sB | a.o_sV) % 4) return false;
   if (a.Z && (!aligned16(a.Z) || (a.z_sB | a.z_sV) % 4)) return false;
   if (a.G && (!aligned16(a.G) || (a.g_sB | a.g_sV) % 4)) return false;
+  if (a.M && (!aligned16(a.M) || (a.m_sB | a.m_sV) % 4)) return false;
   return true;
 }
 

@@ -166,7 +166,10 @@ def plan_for(coo: torch.Tensor) -> SparsePlan:
 
 class ChebConvFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, plan: SparsePlan, act: int = 0):
+    def forward(ctx, x, weight, bias, plan: SparsePlan, act: int = 0, input_is_relu: bool = False, premasked: bool = False):
+        """``input_is_relu``: x is the output of a ReLU whose backward the caller has delegated to this layer — the
+        backward returns dx * [x > 0] (mask applied by the kernel that writes dx).  ``premasked``: this layer's own fused
+        ReLU (act = 1) gets its gradient already masked by its only consumer, so the backward neither masks nor keeps y."""
         _require_cuda_f32(x, "inputs")
         _require_cuda_f32(weight, "weight")
         B, V, Fin = x.shape
@@ -205,11 +208,13 @@ class ChebConvFunction(torch.autograd.Function):
         # act = 1 (ReLU fused into the last kernel of the forward): the backward masks dy with the sign of the
         # output, which is therefore saved — such a layer's output must not be modified in place by the caller
         # (the reference applies its activation out of place, my_models_graph.py:113).
-        ctx.save_for_backward(x, w, *([ws] if keep else []), *([y] if act else []))
+        own_mask = bool(act) and not premasked
+        ctx.save_for_backward(x, w, *([ws] if keep else []), *([y] if own_mask else []))
         ctx.plan = plan
         ctx.has_bias = bias is not None
-        ctx.act = int(act)
+        ctx.act = int(own_mask)
         ctx.keep = bool(keep)
+        ctx.mask_dx = bool(input_is_relu)
         return y
 
     @staticmethod
@@ -227,25 +232,34 @@ class ChebConvFunction(torch.autograd.Function):
         need_dx = ctx.needs_input_grad[0]
         need_dw = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
         if not (need_dx or need_dw):
-            return None, None, None, None, None
+            return None, None, None, None, None, None, None
+        flags = 0
+        post_mask = False
+        if ctx.mask_dx and need_dx:
+            if B == 1 or x.stride(0) == V * x.stride(1):
+                flags = 1  # DSW_BWD_MASK_DX_BY_X
+            else:
+                post_mask = True
         dx = torch.empty((B, V, Fin), dtype=torch.float32, device=x.device) if need_dx else None
         dw = torch.empty_like(w) if need_dw else None
         db = torch.empty(Fout, dtype=torch.float32, device=x.device) if (need_dw and ctx.has_bias) else None
         have_saved = 1 if (terms_ptr is not None or not need_dw) else 0
         with torch.cuda.device(x.device):
             ws = _workspace(lib.dsw_cheb_bwd_workspace_bytes(B, V, Fin, Fout, K, have_saved), x.device)
-            rc = lib.dsw_cheb_bwd(
+            rc = lib.dsw_cheb_bwd_ex(
                 plan.handle, x.data_ptr(), x.stride(0), x.stride(1), dy.data_ptr(), w.data_ptr(), terms_ptr,
                 dx.data_ptr() if dx is not None else None, dw.data_ptr() if dw is not None else None,
-                db.data_ptr() if db is not None else None, B, Fin, Fout, K, ws.data_ptr(), ws.numel(),
+                db.data_ptr() if db is not None else None, B, Fin, Fout, K, flags, ws.data_ptr(), ws.numel(),
                 _stream_ptr(x.device),
             )
-        _lib.check(rc, "dsw_cheb_bwd")
-        return dx, dw, db, None, None
+        _lib.check(rc, "dsw_cheb_bwd_ex")
+        if post_mask:
+            dx = torch.ops.aten.threshold_backward(dx, x, 0.0)
+        return dx, dw, db, None, None, None, None
 
 
-def cheb_conv(x, weight, bias, plan: SparsePlan, act: int = 0):
-    return ChebConvFunction.apply(x, weight, bias, plan, act)
+def cheb_conv(x, weight, bias, plan: SparsePlan, act: int = 0, input_is_relu: bool = False, premasked: bool = False):
+    return ChebConvFunction.apply(x, weight, bias, plan, act, input_is_relu, premasked)
 
 
 def cheb_terms(x: torch.Tensor, plan: SparsePlan, K: int) -> torch.Tensor:

@@ -53,7 +53,7 @@ def _pad4(n: int) -> int:
     return (-n) % 4
 
 
-def _cheb_conv_padded(inputs, weight, bias, plan, act=0):
+def _cheb_conv_padded(inputs, weight, bias, plan, act=0, input_is_relu=False, premasked=False):
     """Channel counts that are not multiples of 4 (21 input features, 2 outputs) would force the
     unaligned scalar kernels (no 16-byte rows, no TMA).  Zero-padding the channel dimension of the
     activations and of ``weight`` / ``bias`` is exact — padded inputs meet zero weights, padded outputs
@@ -61,7 +61,10 @@ def _cheb_conv_padded(inputs, weight, bias, plan, act=0):
     gradients back."""
     pin, pout = _pad4(inputs.shape[2]), _pad4(weight.shape[2])
     if inputs.shape[2] != weight.shape[0] or (pin == 0 and pout == 0):
-        return F_.cheb_conv(inputs, weight, bias, plan, act)  # (a shape mismatch raises the reference's error there)
+        # (a shape mismatch raises the reference's error there)
+        return F_.cheb_conv(inputs, weight, bias, plan, act, input_is_relu, premasked)
+    if input_is_relu or premasked:
+        raise ValueError("the ReLU-mask delegation needs channel counts that are multiples of 4 (see ConvCheb.relu_chain_ok)")
     x = torch.nn.functional.pad(inputs, (0, pin)) if pin else inputs
     w = torch.nn.functional.pad(weight, (0, pout, 0, 0, 0, pin)) if (pin or pout) else weight
     b = torch.nn.functional.pad(bias, (0, pout)) if (bias is not None and pout) else bias
@@ -132,18 +135,33 @@ class ConvCheb(torch.nn.Module):
     # activations ``forward(..., activation=)`` can fuse into the convolution's last kernel
     fused_activations = ("relu",)
 
-    def forward(self, inputs, activation=None):
+    def relu_chain_ok(self) -> bool:
+        """True when this layer can take part in the ReLU-mask delegation of ``forward(..., input_is_relu= / premasked=)``:
+        library convolution, channel counts that need no padding."""
+        return self._conv is conv_cheb and _pad4(self.in_channels) == 0 and _pad4(self.out_channels) == 0
+
+    def forward(self, inputs, activation=None, input_is_relu=False, premasked=False):
         """``forward(inputs)`` is the reference's signature; ``activation="relu"`` (an extension used by
         ``models.ConvBlock``) applies the ReLU inside the convolution's last kernel instead of in a
-        separate element-wise pass."""
+        separate element-wise pass.
+
+        ``input_is_relu`` / ``premasked`` (extensions used by ``models.ResBlock``) move the ReLU's backward from a
+        separate element-wise pass into the NEXT layer's input-gradient kernel: a layer called with
+        ``activation="relu", premasked=True`` promises that its output feeds exactly one layer, which is called with
+        ``input_is_relu=True`` and returns the gradient already multiplied by ``[x > 0]``."""
         if activation not in (None,) + self.fused_activations:
             raise ValueError(f"activation {activation!r} cannot be fused; apply it to the output instead")
         if self._conv is not conv_cheb:  # user-supplied convolution: honour the reference contract
+            if input_is_relu or premasked:
+                raise ValueError("the ReLU-mask delegation needs the library convolution")
             out = self._conv(self.laplacian, inputs, self.weight)
             if self.bias is not None:
                 out += self.bias
             return torch.relu(out) if activation == "relu" else out
-        return _cheb_conv_padded(inputs, self.weight, self.bias, F_.plan_for(self.laplacian), 1 if activation == "relu" else 0)
+        if premasked and activation != "relu":
+            raise ValueError("premasked=True only makes sense with activation='relu'")
+        return _cheb_conv_padded(inputs, self.weight, self.bias, F_.plan_for(self.laplacian), 1 if activation == "relu" else 0,
+                                 input_is_relu, premasked)
 
 
 class NodeLinear(torch.nn.Linear):

@@ -78,7 +78,15 @@ class ConvBlock(torch.nn.Module):
     def _bn(self, x):
         return self.bn(x.permute(0, 2, 1)).permute(0, 2, 1)
 
-    def forward(self, x):
+    def relu_chain_ok(self) -> bool:
+        """This block is a library convolution (+ fused ReLU) and nothing else, on aligned channel counts: it can take
+        part in the ReLU-mask delegation (``layers.ConvCheb.forward``)."""
+        ok = getattr(self.conv, "relu_chain_ok", None)
+        return bool(ok and ok() and not self.norm and (self._fused_act == "relu" or not self.act))
+
+    def forward(self, x, input_is_relu=False, premasked=False):
+        if input_is_relu or premasked:  # (only requested by ResBlock after relu_chain_ok())
+            return self.conv(x, activation=self._fused_act, input_is_relu=input_is_relu, premasked=premasked)
         if self._fused_act is not None:
             x = self.conv(x, activation=self._fused_act)
             return self._bn(x) if self.norm else x
@@ -128,6 +136,21 @@ class ResBlock(torch.nn.Module):
             torch.nn.init.constant_(last.bn.weight, 0)
             torch.nn.init.constant_(last.bn.bias, 0)
 
+    def _run_convs(self, out):
+        """The block's ConvBlocks in sequence.  Where block i ends in a fused ReLU and block i + 1 is a plain library
+        convolution, the ReLU's backward is delegated to block i + 1's input-gradient kernel (no threshold pass)."""
+        blocks = [getattr(self, name) for name in self.conv_names_list]
+        relu_in = False
+        for i, blk in enumerate(blocks):
+            delegate = (_FUSED_SKIPS and i + 1 < len(blocks) and torch.is_grad_enabled()
+                        and getattr(blk, "_fused_act", None) == "relu" and blk.relu_chain_ok() and blocks[i + 1].relu_chain_ok())
+            if relu_in or delegate:
+                out = blk(out, input_is_relu=relu_in, premasked=delegate)
+            else:
+                out = blk(out)
+            relu_in = delegate
+        return out
+
     def forward(self, x, cat_slot=False):
         """``cat_slot=True`` (an extension used by ``UNetSpherical.encode``): the output is written as the second half of
         a ``[B, V, 2C]`` buffer, ready for the decoder's skip concatenation (``layers.unpool_cat``)."""
@@ -140,12 +163,9 @@ class ResBlock(torch.nn.Module):
             out = x
             if torch.is_grad_enabled() and x.requires_grad:
                 out, state = self._fork(x)
-            for name in self.conv_names_list:
-                out = getattr(self, name)(out)
+            out = self._run_convs(out)
             return self.res_connection.forward_rezero(x, out, self.rezero_weight, cat_slot=cat_slot, fork_state=state)
-        out = x
-        for name in self.conv_names_list:
-            out = getattr(self, name)(out)
+        out = self._run_convs(x)
         if self.rezero and self._fused_tail is not None:
             if one_launch:
                 return self.res_connection.forward_rezero(x, out, self.rezero_weight, cat_slot=cat_slot and _FUSED_SKIPS)

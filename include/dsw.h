@@ -116,6 +116,16 @@ int dsw_cheb_bwd(const dsw_plan* lap, const float* x, int64_t x_sB, int64_t x_sV
                  const float* W, const float* saved_terms, float* dx, float* dW, float* dbias, int32_t B,
                  int32_t Fin, int32_t Fout, int32_t K, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same with flags.  DSW_BWD_MASK_DX_BY_X: the layer's input x is the output of a ReLU (ConvBlock.forward,
+ * my_models_graph.py:104-118, feeding the next ConvBlock of a ResBlock, :205-209), so the gradient that continues upstream is
+ * dx * [x > 0] (torch: threshold_backward in a separate pass): the mask is applied by the kernel that writes dx (channel-mix
+ * epilogue or last hop).  Needs x (with B > 1: x_sB == V * x_sV, else DSW_ERR_UNSUPPORTED). */
+#define DSW_BWD_MASK_DX_BY_X 1
+int dsw_cheb_bwd_ex(const dsw_plan* lap, const float* x, int64_t x_sB, int64_t x_sV, const float* dy,
+                    const float* W, const float* saved_terms, float* dx, float* dW, float* dbias, int32_t B,
+                    int32_t Fin, int32_t Fout, int32_t K, int32_t flags, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
 /* The two halves on their own (thin wrappers over dsw_cheb_bwd). */
 size_t dsw_cheb_bwd_data_workspace_bytes(int32_t B, int32_t V, int32_t Fin, int32_t Fout, int32_t K);
 int dsw_cheb_bwd_data(const dsw_plan* lap, const float* dy, const float* W, float* dx, int32_t B,

@@ -1086,3 +1086,36 @@ def test_unet_fused_skips_match_plain_composition(dev, lib):
     assert rel_err(yf, yp) < 1e-5 and rel_err(dxf, dxp) < 1e-5
     for n in gp:
         assert rel_err(gf[n], gp[n]) < 1e-5, n
+
+
+@pytest.mark.parametrize("F0,F1,F2,K", [(32, 64, 32, 4), (64, 32, 96, 3), (16, 48, 48, 1), (128, 64, 8, 4)])
+@pytest.mark.parametrize("bwd_algo", [0, 1, 2], ids=["auto", "terms", "clenshaw"])
+def test_relu_mask_delegated_to_the_next_layer_matches_threshold_pass(F0, F1, F2, K, bwd_algo, dev, lib, mix_mode):
+    """conv -> ReLU -> conv (ConvBlock chain of a ResBlock, my_models_graph.py:104-118, 205-209): with the ReLU's backward
+    delegated to the second layer's input-gradient kernel (channel-mix epilogue or last Clenshaw hop, DSW_BWD_MASK_DX_BY_X)
+    every gradient equals the plain path's, which masks dy in a separate threshold pass."""
+    from deepsphere_weather_b200 import graphs as G
+    from deepsphere_weather_b200 import layers as L
+
+    torch.manual_seed(17)
+    lap = G.healpix_laplacian(8)
+    c1, c2 = L.ConvCheb(F0, F1, K, lap).to(dev), L.ConvCheb(F1, F2, K, lap).to(dev)
+    with torch.no_grad():
+        c1.bias.normal_(0, 0.3), c2.bias.normal_(0, 0.3)
+    x = torch.randn(3, 768, F0, device=dev)
+    g = torch.randn(3, 768, F2, device=dev)
+    lib.dsw_set_option(5, bwd_algo)
+    try:
+        res = []
+        for delegated in (False, True):
+            xi = x.clone().requires_grad_(True)
+            c1.zero_grad(set_to_none=True), c2.zero_grad(set_to_none=True)
+            h = c1(xi, activation="relu", premasked=delegated)
+            y = c2(h, input_is_relu=delegated)
+            y.backward(g)
+            res.append([y.detach(), xi.grad] + [p.grad.clone() for p in list(c1.parameters()) + list(c2.parameters())])
+    finally:
+        lib.dsw_set_option(5, 0)
+    for a, b in zip(*res):
+        assert rel_err(b, a) < 1e-6
+    assert (res[1][1] != 0).any()
