@@ -81,6 +81,7 @@ SIGNATURES = {
     "dsw_debug_counters": (C.c_int, [_ptr, C.c_int]),
     "dsw_debug_dense_counters": (C.c_int, [_ptr, C.c_int]),
     "dsw_debug_chain_counters": (C.c_int, [_ptr, C.c_int]),
+    "dsw_debug_mix_counters": (C.c_int, [_ptr, C.c_int]),
     "dsw_set_option": (C.c_int, [C.c_int, _i64]),
     "dsw_get_option": (_i64, [C.c_int]),
 }

@@ -475,6 +475,12 @@ constexpr int EPI_PITCH = 64;                          // floats per staged row;
 constexpr int EPI_BYTES = 32 * EPI_PITCH * 4;          // one warp's 32 x 64 staging chunk
 __device__ __forceinline__ int epi_off(int row, int chunk) { return row * EPI_PITCH + ((chunk ^ (row & 15)) << 2); }
 
+// Role timing for tuning (DSW_OPT_DEBUG bit 2048): cycles summed over CTAs, read by dsw_debug_mix_counters:
+// [0] producer waiting for a free stage, [1] converter warp 0 waiting for the TMA, [2] converting, [3] MMA issuer waiting
+// for a free accumulator, [4] MMA issuer waiting for operands, [5] epilogue warp 0 waiting for the accumulator,
+// [6] its TMEM -> shared-memory phase, [7] its store phase, [8] tiles, [9] kernel cycles (CTA 0).
+__device__ unsigned long long g_mix_prof[16];
+
 // ADDEND: the epilogue also adds r_scale * R (MixArgs); a separate instantiation so that the plain kernel's
 // register allocation is untouched.
 template <bool ADDEND>
@@ -524,6 +530,8 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
   pdl_wait();  // barriers and TMEM are set up; the operands may still be being written by the previous kernel
+  const bool prof = (P.dbg & 2048) != 0;
+  const long long t_start = prof ? clock64() : 0;
 
   const int total_kb = a.P * P.nkb;
   const int last_ksteps = (a.Ka - (P.nkb - 1) * BKB + 15) / 16;  // K-steps (of 16) in a plane's last block
@@ -536,12 +544,17 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
   if (warp < N_CONV_WARPS) {
     // ================= converters: raw fp32 block (shared) -> bf16 hi / lo images, in place =================
     const int q = t & 15;
+    int s = -1;
+    uint32_t ph = 1;  // (stage, phase) advance without 64-bit divisions
     for (int64_t it = 0; it < n_iters; ++it) {
-      const int s = (int)(it % S);
-      const uint32_t ph = (uint32_t)(it / S) & 1;
+      if (++s == S) s = 0;
+      if (s == 0) ph ^= 1;
       uint8_t* Ahi = smem_gen + (size_t)s * stage_bytes;
       uint8_t* Alo = Ahi + A_TILE;
+      const long long tc0 = (prof && t == 0) ? clock64() : 0;
       mbar_wait(raw_full(s), ph);
+      const long long tc1 = (prof && t == 0) ? clock64() : 0;
+      if (prof && t == 0) atomicAdd(&g_mix_prof[1], (unsigned long long)(tc1 - tc0));
       if (P.dbg & 128) {  // timing experiment: no conversion
         if (lane == 0) mbar_arrive(a_full(s));
         continue;
@@ -562,19 +575,26 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
       fence_proxy_async();  // generic-proxy stores -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full(s));
+      if (prof && t == 0) atomicAdd(&g_mix_prof[2], (unsigned long long)(clock64() - tc1));
     }
   } else if (warp == WARP_BLOAD) {
     // ================= producer (one thread): TMA of the raw A block + bulk copy of the B images =================
     if (lane == 0) {
-      int64_t it = 0;
+      int s = -1;
+      uint32_t use = 0xffffffffu;
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int ctile = (int)(tile % n_ctiles);
-        const int64_t n0 = (tile / n_ctiles) * BM;
+        const int64_t rtile = n_ctiles == 1 ? tile : tile / n_ctiles;
+        const int ctile = n_ctiles == 1 ? 0 : (int)(tile - rtile * n_ctiles);
+        const int64_t n0 = rtile * BM;
         const uint8_t* bsrc = P.bprep + (int64_t)ctile * total_kb * 2 * b_img;
-        for (int kbi = 0; kbi < total_kb; ++kbi, ++it) {
-          const int s = (int)(it % S);
-          const uint32_t use = (uint32_t)(it / S);
-          if (use > 0) mbar_wait(empty(s), (use - 1) & 1);
+        for (int kbi = 0; kbi < total_kb; ++kbi) {
+          if (++s == S) s = 0;
+          if (s == 0) ++use;
+          if (use > 0) {
+            const long long tq = prof ? clock64() : 0;
+            mbar_wait(empty(s), (use - 1) & 1);
+            if (prof) atomicAdd(&g_mix_prof[0], (unsigned long long)(clock64() - tq));
+          }
           const int p = kbi / P.nkb, kb = kbi - p * P.nkb;
           const uint32_t st_base = smem_base + s * stage_bytes;
           if (P.dbg & 32) {  // timing experiment: no A transfer
@@ -601,21 +621,26 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
     // ================= MMA issuer (one thread) =================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      int64_t it = 0;
+      int s = -1;
+      uint32_t ph = 1;
       for (int64_t lt = 0; lt < my_tiles; ++lt) {
         const int buf = (int)(lt & 1);
         const uint32_t buse = (uint32_t)(lt >> 1);
         if (buse > 0) {
+          const long long tm = prof ? clock64() : 0;
           mbar_wait(acc_empty(buf), (buse - 1) & 1);
           tc_fence_after();
+          if (prof) atomicAdd(&g_mix_prof[3], (unsigned long long)(clock64() - tm));
         }
         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * P.tmem_cols);
-        for (int kbi = 0; kbi < total_kb; ++kbi, ++it) {
-          const int s = (int)(it % S);
-          const uint32_t ph = (uint32_t)(it / S) & 1;
+        for (int kbi = 0; kbi < total_kb; ++kbi) {
+          if (++s == S) s = 0;
+          if (s == 0) ph ^= 1;
+          const long long tm = prof ? clock64() : 0;
           mbar_wait(a_full(s), ph);
           mbar_wait(b_full(s), ph);
           tc_fence_after();
+          if (prof) atomicAdd(&g_mix_prof[4], (unsigned long long)(clock64() - tm));
           const uint32_t st_base = smem_base + s * stage_bytes;
           const int kb = kbi % P.nkb;
           const int ksteps = (kb == P.nkb - 1) ? last_ksteps : BKB / 16;
@@ -639,53 +664,68 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
     const bool vec_ok = (a.Cw % 4 == 0) && (a.ldc % 4 == 0) && (a.sCp % 4 == 0) &&
                         ((reinterpret_cast<uintptr_t>(a.C) & 15) == 0);
     const int half = lane >> 4, c4 = lane & 15;  // store phase: two rows per instruction, 16 lanes x float4 per row
+    const bool single_plane = a.Cw >= a.Nc;
     // ADDEND: the epilogue is bound by the latency of its addend loads (short-K mixes: 8 KB in flight per SM).  Each warp
     // pulls the addend rows of its NEXT tile into L2 a whole tile ahead (one row per lane, a 128-byte line per prefetch).
     auto prefetch_addend = [&](int64_t lt_next) {
       if (!ADDEND || a.R == nullptr || lt_next >= my_tiles || (P.dbg & 1024)) return;
       const int64_t tile_n = blockIdx.x + lt_next * gridDim.x;
-      const int64_t n = (tile_n / n_ctiles) * BM + quarter * 32 + lane;
-      const int c0 = (int)(tile_n % n_ctiles) * BN;
+      const int64_t rt_n = n_ctiles == 1 ? tile_n : tile_n / n_ctiles;
+      const int64_t n = rt_n * BM + quarter * 32 + lane;
+      const int c0 = (int)(tile_n - rt_n * n_ctiles) * BN;
       if (n >= a.N) return;
       const float* p = a.R + n * a.ldr + c0;
       const int ncols = min(BN, a.Nc - c0);
       for (int c = 0; c < ncols; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + c));
     };
     prefetch_addend(0);
+    const float rs_all = (ADDEND && a.r_scale != nullptr) ? __ldg(a.r_scale) : 1.f;
     for (int64_t lt = 0; lt < my_tiles; ++lt) {
       const int64_t tile = blockIdx.x + lt * gridDim.x;
       const int buf = (int)(lt & 1);
       const uint32_t ph = (uint32_t)(lt >> 1) & 1;
-      const int ctile = (int)(tile % n_ctiles);
-      const int64_t row0 = (tile / n_ctiles) * BM + quarter * 32;  // first output row of this warp
+      const int64_t rtile = n_ctiles == 1 ? tile : tile / n_ctiles;
+      const int ctile = n_ctiles == 1 ? 0 : (int)(tile - rtile * n_ctiles);
+      const int64_t row0 = rtile * BM + quarter * 32;  // first output row of this warp
       prefetch_addend(lt + 1);
+      const bool ep = prof && quarter == 0 && lane == 0;
+      long long te0 = ep ? clock64() : 0, te_ld = 0, te_st = 0;
       mbar_wait(acc_full(buf), ph);
       tc_fence_after();
+      if (ep) atomicAdd(&g_mix_prof[5], (unsigned long long)(clock64() - te0)), atomicAdd(&g_mix_prof[8], 1ull);
       const uint32_t t_addr = tmem_base + (uint32_t)(buf * P.tmem_cols) + ((uint32_t)(quarter * 32) << 16);
       for (int cg = 0; cg < BN; cg += 64) {
         const int ncol = min(64, BN - cg);  // multiple of 16 (warp-uniform)
         // columns of this lane in the store phase
         const int col = ctile * BN + cg + c4 * 4;
         const bool col_ok = (c4 * 4 < ncol) && (col < a.Nc);
-        // ADDEND: the 16 addend row segments of this lane are loaded in two batches of 8 that are in flight while the
-        // accumulator chunk moves TMEM -> shared memory (first batch) and while the first batch is consumed (second)
-        float4 rv[16];
+        // the bias values of this lane's columns: requested before the accumulator chunk is fetched, so that their
+        // latency (a dependent global load per chunk: ~500 cycles, a third of a short-K tile's epilogue) is hidden
+        float bv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (col_ok && a.bias != nullptr) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (col + e < a.bias_n) bv[e] = __ldg(a.bias + col + e);
+        }
+        // ADDEND: the addend row segments of this lane (16 rows x 16 bytes) are requested in two batches of 8: the first
+        // before the accumulator chunk moves TMEM -> shared memory, the second one by one as the first is consumed.  Only
+        // whole 32-row blocks take this path (the last, partial tile falls through to the scalar tail): the epilogue
+        // warps run alone on their schedulers, so the loop is bound by its instruction count and register pressure.
+        float4 rv[8];
         bool addend_vec = false;
         const float* r_row = nullptr;
         if (ADDEND) {
-          const int ccol0 = col % a.Cw;
+          const int ccol0 = single_plane ? col : col % a.Cw;
           addend_vec = col_ok && a.R != nullptr && vec_ok && (col + 3 < a.Nc) && (ccol0 + 3 < a.Cw) && (a.ldr % 4 == 0) &&
-                       ((reinterpret_cast<uintptr_t>(a.R) & 15) == 0);
+                       ((reinterpret_cast<uintptr_t>(a.R) & 15) == 0) && (row0 + 32 <= a.N) && a.act == 0;
           if (addend_vec) {
             r_row = a.R + (row0 + half) * a.ldr + col;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (row0 + half + 2 * i < a.N) rv[i] = __ldg(reinterpret_cast<const float4*>(r_row + (int64_t)(2 * i) * a.ldr));
-            }
+            for (int i = 0; i < 8; ++i) rv[i] = __ldg(reinterpret_cast<const float4*>(r_row + (int64_t)(2 * i) * a.ldr));
           }
         }
         // TMEM loads two chunks (32 columns) at a time, one wait per pair
+        if (ep) te0 = clock64();
 #pragma unroll
         for (int hq = 0; hq < 2; ++hq) {
           if (hq * 32 >= ncol) break;
@@ -703,46 +743,36 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
             }
         }
         __syncwarp();
+        if (ep) te_ld += clock64() - te0, te0 = clock64();
         if (col_ok) {
-          float bv[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (a.bias && col + e < a.bias_n) bv[e] = __ldg(a.bias + col + e);
-          const int cp = col / a.Cw, ccol = col - cp * a.Cw;
+          const int cp = single_plane ? 0 : col / a.Cw, ccol = col - cp * a.Cw;
           const bool vec = vec_ok && (col + 3 < a.Nc) && (ccol + 3 < a.Cw);
           float* cbase = a.C + (int64_t)cp * a.sCp + ccol;
           const bool relu = a.act == 1;
           if (ADDEND && addend_vec) {
-            // same, plus the addend row segments (C += r_scale * R)
-            const float rs = a.r_scale ? __ldg(a.r_scale) : 1.f;
+            // same, plus the addend row segments (C += r_scale * R, or the ReLU mask C = R > 0 ? C : 0)
+            const float rs = rs_all;
             const bool mask_mode = a.r_mode == 1;
             float* cp_row = cbase + (row0 + half) * a.ldc;
             const int64_t step = 2 * (int64_t)a.ldc;
-            int64_t n = row0 + half;
 #pragma unroll
-            for (int i = 8; i < 16; ++i) {  // second batch of addend loads
-              rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (row0 + half + 2 * i < a.N) rv[i] = __ldg(reinterpret_cast<const float4*>(r_row + (int64_t)(2 * i) * a.ldr));
-            }
+            for (int h8 = 0; h8 < 2; ++h8) {
+              float4 v[8];
 #pragma unroll
-            for (int i0 = 0; i0 < 16; i0 += 4) {
-              float4 v[4];
+              for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(stg + epi_off(2 * (h8 * 8 + i) + half, c4));
 #pragma unroll
-              for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(stg + epi_off(2 * (i0 + i) + half, c4));
-#pragma unroll
-              for (int i = 0; i < 4; ++i, n += 2, cp_row += step) {
-                if (n >= a.N) continue;
-                float4 o = v[i];
-                const float4 r4 = rv[i0 + i];
-                if (mask_mode) {  // ReLU mask of a gradient by the ReLU's output
-                  o.x = r4.x > 0.f ? o.x + bv[0] : 0.f, o.y = r4.y > 0.f ? o.y + bv[1] : 0.f;
-                  o.z = r4.z > 0.f ? o.z + bv[2] : 0.f, o.w = r4.w > 0.f ? o.w + bv[3] : 0.f;
+              for (int i = 0; i < 8; ++i) {
+                const float4 r4 = rv[i];
+                if (h8 == 0) rv[i] = __ldg(reinterpret_cast<const float4*>(r_row + (int64_t)(2 * (8 + i)) * a.ldr));
+                float4 o;
+                if (mask_mode) {
+                  o = make_float4(r4.x > 0.f ? v[i].x + bv[0] : 0.f, r4.y > 0.f ? v[i].y + bv[1] : 0.f,
+                                  r4.z > 0.f ? v[i].z + bv[2] : 0.f, r4.w > 0.f ? v[i].w + bv[3] : 0.f);
                 } else {
-                  o.x = fmaf(rs, r4.x, o.x + bv[0]), o.y = fmaf(rs, r4.y, o.y + bv[1]);
-                  o.z = fmaf(rs, r4.z, o.z + bv[2]), o.w = fmaf(rs, r4.w, o.w + bv[3]);
+                  o = make_float4(fmaf(rs, r4.x, v[i].x + bv[0]), fmaf(rs, r4.y, v[i].y + bv[1]),
+                                  fmaf(rs, r4.z, v[i].z + bv[2]), fmaf(rs, r4.w, v[i].w + bv[3]));
                 }
-                if (relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
-                *reinterpret_cast<float4*>(cp_row) = o;
+                if (!(P.dbg & 16)) *reinterpret_cast<float4*>(cp_row + (int64_t)(h8 * 8 + i) * step) = o;
               }
             }
           } else if (vec && !(ADDEND && a.R != nullptr)) {
@@ -750,6 +780,30 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
             float* cp_row = cbase + (row0 + half) * a.ldc;
             const int64_t step = 2 * (int64_t)a.ldc;
             int64_t n = row0 + half;
+            if (row0 + 32 <= a.N && !(P.dbg & 16)) {
+              // whole 32-row block in range (every tile but the last): no per-row checks.  The epilogue warps run alone on
+              // their schedulers, so this loop is bound by its instruction count (measured: 325 -> ~150 per chunk).
+#pragma unroll
+              for (int i0 = 0; i0 < 16; i0 += 8) {
+                float4 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const float4*>(stg + epi_off(2 * (i0 + i) + half, c4));
+                if (relu) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float4 o = make_float4(fmaxf(v[i].x + bv[0], 0.f), fmaxf(v[i].y + bv[1], 0.f),
+                                                 fmaxf(v[i].z + bv[2], 0.f), fmaxf(v[i].w + bv[3], 0.f));
+                    *reinterpret_cast<float4*>(cp_row + (int64_t)(i0 + i) * step) = o;
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float4 o = make_float4(v[i].x + bv[0], v[i].y + bv[1], v[i].z + bv[2], v[i].w + bv[3]);
+                    *reinterpret_cast<float4*>(cp_row + (int64_t)(i0 + i) * step) = o;
+                  }
+                }
+              }
+            } else
 #pragma unroll
             for (int i0 = 0; i0 < 16; i0 += 8) {
               float4 v[8];
@@ -785,14 +839,17 @@ __global__ void __launch_bounds__(THREADS2, 1) mix_tma_kernel(const __grid_const
           }
         }
         __syncwarp();
+        if (ep) te_st += clock64() - te0;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(buf));
+      if (ep) atomicAdd(&g_mix_prof[6], (unsigned long long)te_ld), atomicAdd(&g_mix_prof[7], (unsigned long long)te_st);
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (prof && t == 0 && blockIdx.x == 0) atomicAdd(&g_mix_prof[9], (unsigned long long)(clock64() - t_start));
   if (warp == WARP_MMA) tmem_dealloc(tmem_base, (uint32_t)(2 * P.tmem_cols));
 }
 
@@ -866,7 +923,7 @@ int launch_mix_tc_ws(const MixArgs& a, void* prep, size_t prep_bytes, bool do_pr
   P.m = a;
   P.BN = std::min(mix_bn_max(), (a.Nc + 15) / 16 * 16);
   P.nkb = (a.Ka + tc::BKB - 1) / tc::BKB;
-  P.dbg = (int)g_options[DSW_OPT_DEBUG].load(std::memory_order_relaxed) & 0x5F0;
+  P.dbg = (int)g_options[DSW_OPT_DEBUG].load(std::memory_order_relaxed) & 0xDF0;
   P.cmode = split_mode();
   int cols = 32;
   while (cols < P.BN) cols <<= 1;
@@ -927,3 +984,15 @@ int launch_mix_tc_ws(const MixArgs& a, void* prep, size_t prep_bytes, bool do_pr
 }
 
 }  // namespace dsw
+
+extern "C" int dsw_debug_mix_counters(uint64_t* out16, int reset) {
+  if (!out16) return DSW_ERR_BAD_ARGUMENT;
+  unsigned long long h[16];
+  DSW_CUDA_TRY(cudaMemcpyFromSymbol(h, dsw::tc::g_mix_prof, sizeof(h)));
+  for (int i = 0; i < 16; ++i) out16[i] = h[i];
+  if (reset) {
+    unsigned long long z[16] = {};
+    DSW_CUDA_TRY(cudaMemcpyToSymbol(dsw::tc::g_mix_prof, z, sizeof(z)));
+  }
+  return DSW_OK;
+}

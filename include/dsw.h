@@ -350,6 +350,11 @@ int dsw_debug_counters(uint64_t* out8, int reset);
 /* Tuning only: with DSW_OPT_DEBUG bit 512 the weight-gradient kernel sums role cycles over its CTAs (converters
  * waiting for the TMA, converting, stage count, producer waiting for a free stage, MMA issuer waiting). */
 int dsw_debug_dense_counters(uint64_t* out8, int reset);
+/* Tuning only: with DSW_OPT_DEBUG bit 2048 the TMA-fed channel mix sums role cycles over its CTAs: [0] producer waiting for
+ * a free stage, [1] converters waiting for the TMA, [2] converting, [3] MMA issuer waiting for a free accumulator, [4] ...
+ * for operands, [5] epilogue waiting for the accumulator, [6] its TMEM -> shared-memory phase, [7] its store phase,
+ * [8] tiles, [9] kernel cycles of CTA 0. */
+int dsw_debug_mix_counters(uint64_t* out16, int reset);
 /* Tuning only: with DSW_OPT_DEBUG = 4 the fused chain kernel sums per-phase SM cycles: [0..4] over its compute
  * teams (wait for the next item, Z/G loads + wait for the transfers, entry loop, stores, item count), [8..15] over
  * its control warps (metadata, wait for the loop end, issue, wait for the stores, fence + flag, blocking dependency

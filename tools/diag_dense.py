@@ -43,7 +43,10 @@ def main():
                 ("BN128", 0, 128), ("cvt-F2F", 0, -1), ("cvt-int", 0, -2)]
     print("== channel mix (dsw_linear_fwd): us per call")
     print(f"{'Fin->Fout':>12s} " + " ".join(f"{n:>9s}" for n, _, _ in variants) + "   floorHBM floorMMA")
-    for Fin, Fout in [(256, 512), (256, 128), (512, 256), (128, 256), (64, 256), (64, 64), (256, 64)]:
+    shapes = [(256, 512), (256, 128), (512, 256), (128, 256), (64, 256), (64, 64), (256, 64)]
+    if os.environ.get("DIAG_SHAPES"):  # e.g. DIAG_SHAPES=24x128,64x256
+        shapes = [tuple(int(v) for v in s_.split("x")) for s_ in os.environ["DIAG_SHAPES"].split(",")]
+    for Fin, Fout in shapes:
         x = torch.randn(B, V, Fin, device=dev)
         w = torch.randn(Fout, Fin, device=dev) * 0.05
         b = torch.randn(Fout, device=dev)
@@ -67,6 +70,8 @@ def main():
         print(f"{Fin:5d}->{Fout:<5d} " + " ".join(f"{t:9.1f}" for t in row) + f"   {hbm:8.1f} {mma:8.1f}", flush=True)
         del x, y
 
+    if os.environ.get("DIAG_MIX_ONLY"):
+        return
     wvariants = [("base", 0), ("no-A", 32), ("no-B", 64), ("no-AB", 96), ("no-conv", 128), ("no-mma", 256),
                  ("mma-only", 32 | 64 | 128), ("none", 32 | 64 | 128 | 256), ("cvt-F2F", -1), ("cvt-int", -2)]
     print("== weight gradient (dsw_linear_bwd, dW only): us per call;  M side = dy channels, N side = x channels")

@@ -57,11 +57,11 @@ def main():
             cnt[name] += 1
             spans.append((ev.time_range.start, ev.time_range.end))
     sub = os.environ.get("KINETO_LIST")
-    if sub:  # per-launch durations (us) of the kernels whose name contains KINETO_LIST, first profiled step only
+    for one in (sub.split(",") if sub else []):  # per-launch durations (us) of the kernels whose name contains it, first step
         evs = sorted((ev.time_range.start, ev.device_time, ev.name) for ev in prof.events()
-                     if ev.device_type == torch.autograd.DeviceType.CUDA and sub in ev.name)
+                     if ev.device_type == torch.autograd.DeviceType.CUDA and one in ev.name)
         evs = evs[: len(evs) // steps]
-        print("# per-launch", sub, [round(d, 1) for _, d, _ in evs])
+        print("# per-launch", one, [round(d, 1) for _, d, _ in evs])
     spans.sort()
     busy, cur_s, cur_e = 0.0, None, None
     for s, e in spans:
