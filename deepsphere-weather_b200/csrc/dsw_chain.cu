@@ -186,6 +186,10 @@ __device__ __forceinline__ void st_volatile_s(void* p, uint32_t v) {
 
 }  // namespace
 
+// MASK: the hops may carry a ReLU mask operand (ChainHop::M).  A separate instantiation: the plain kernel's code
+// generation is sensitive to anything added to its store loop (measured: 808 -> 888 us at the metric shape with the
+// masked store compiled in, although no hop used it).
+template <bool MASK>
 __global__ void __launch_bounds__(CH_THREADS, 1)
     hop_chain_kernel(const ChainPlan P, const __grid_constant__ ChainArgs A, const __grid_constant__ ChainMaps maps) {
   extern __shared__ __align__(1024) uint8_t ch_smem[];
@@ -509,7 +513,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
             if (ch[j] >= slab_f) continue;
             float4 o = make_float4(H.alpha * acc[r][j].x, H.alpha * acc[r][j].y, H.alpha * acc[r][j].z, H.alpha * acc[r][j].w);
             if (H.act) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
-            if (H.M != nullptr) {  // ReLU mask of a gradient by the ReLU's output (indexed like the output rows)
+            if (MASK && H.M != nullptr) {  // ReLU mask of a gradient by the ReLU's output (indexed like the output rows)
               const float4 m = ldcg4(H.M + d.b * H.m_sB + (int64_t)row * H.m_sV + d.slab * 64 + ch[j]);
               o.x = m.x > 0.f ? o.x : 0.f, o.y = m.y > 0.f ? o.y : 0.f, o.z = m.z > 0.f ? o.z : 0.f, o.w = m.w > 0.f ? o.w : 0.f;
             }
@@ -651,9 +655,16 @@ static int launch_chain_fused(const dsw_csr& A, const dsw_rb& rb, const ChainHop
     for (int q = 0; q < 8; ++q) maps.m[j][q] = maps.m[0][q];
   }
 
-  static PerDeviceOnce attr_set;
-  DSW_CUDA_TRY(attr_set.max_dynamic_smem(hop_chain_kernel, 227 * 1024));
-  DSW_CUDA_TRY(launch_pdl(hop_chain_kernel, dim3(P.n_ctas), dim3(CH_THREADS), smem, st, pdl_enabled(), P, args, maps));
+  bool any_mask = false;
+  for (int j = 0; j < n; ++j) any_mask = any_mask || hops[j].M != nullptr;
+  static PerDeviceOnce attr_set[2];
+  if (any_mask) {
+    DSW_CUDA_TRY(attr_set[1].max_dynamic_smem(hop_chain_kernel<true>, 227 * 1024));
+    DSW_CUDA_TRY(launch_pdl(hop_chain_kernel<true>, dim3(P.n_ctas), dim3(CH_THREADS), smem, st, pdl_enabled(), P, args, maps));
+  } else {
+    DSW_CUDA_TRY(attr_set[0].max_dynamic_smem(hop_chain_kernel<false>, 227 * 1024));
+    DSW_CUDA_TRY(launch_pdl(hop_chain_kernel<false>, dim3(P.n_ctas), dim3(CH_THREADS), smem, st, pdl_enabled(), P, args, maps));
+  }
   return check_launch();
 }
 

@@ -702,10 +702,6 @@ __global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
           const int64_t col = (int64_t)slab * 64 + ch[j];
           float4 o = make_float4(a.alpha * acc[r][j].x, a.alpha * acc[r][j].y, a.alpha * acc[r][j].z, a.alpha * acc[r][j].w);
           if (a.act) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
-          if (a.M) {  // ReLU mask of a gradient by the ReLU's output (indexed like the output rows)
-            const float4 m = ldg4(a.M + b * a.m_sB + row * a.m_sV + col);
-            o.x = m.x > 0.f ? o.x : 0.f, o.y = m.y > 0.f ? o.y : 0.f, o.z = m.z > 0.f ? o.z : 0.f, o.w = m.w > 0.f ? o.w : 0.f;
-          }
           *reinterpret_cast<float4*>(a.O + b * a.o_sB + row * a.o_sV + col) = o;
         }
       }
@@ -756,7 +752,9 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
   // mostly padding, the plain CSR kernel moves only the real channels
   const int64_t small_f_opt = g_options[DSW_OPT_HOP_SMALL_F].load(std::memory_order_relaxed);
   const int small_f = small_f_opt > 0 ? (int)small_f_opt : 8;
-  if (v4 && rb.R == 4 && hop_mode == 0 && rb.n_tiles > 0 && a.F > small_f) {
+  // (a masked hop — one per step: the last Clenshaw hop of a ReLU-fed layer's backward — takes the row-block kernel below:
+  //  the masked store compiled into the team kernel cost every launch 1-3 %)
+  if (v4 && rb.R == 4 && hop_mode == 0 && rb.n_tiles > 0 && a.F > small_f && a.M == nullptr) {
     const size_t panels = (size_t)(rb.tile_len_max + PANEL_PAD) * DSW_TILE_BLOCKS * 20 + (size_t)((rb.tile_rows_max + 1) & ~1) * 4 +
                           (size_t)((rb.tile_pieces_max + 1) & ~1) * 4 + 8 * MAX_TEAMS + 64;
     const size_t xbuf = (size_t)rb.tile_rows_max * 256;

@@ -63,12 +63,12 @@ def _cheb_conv_padded(inputs, weight, bias, plan, act=0, input_is_relu=False, pr
     if inputs.shape[2] != weight.shape[0] or (pin == 0 and pout == 0):
         # (a shape mismatch raises the reference's error there)
         return F_.cheb_conv(inputs, weight, bias, plan, act, input_is_relu, premasked)
-    if input_is_relu or premasked:
+    if input_is_relu or (premasked and pout):
         raise ValueError("the ReLU-mask delegation needs channel counts that are multiples of 4 (see ConvCheb.relu_chain_ok)")
     x = torch.nn.functional.pad(inputs, (0, pin)) if pin else inputs
     w = torch.nn.functional.pad(weight, (0, pout, 0, 0, 0, pin)) if (pin or pout) else weight
     b = torch.nn.functional.pad(bias, (0, pout)) if (bias is not None and pout) else bias
-    y = F_.cheb_conv(x, w, b, plan, act)
+    y = F_.cheb_conv(x, w, b, plan, act, False, premasked)  # (a padded INPUT does not touch the output the next layer masks by)
     return y[..., : weight.shape[2]] if pout else y
 
 
@@ -135,10 +135,12 @@ class ConvCheb(torch.nn.Module):
     # activations ``forward(..., activation=)`` can fuse into the convolution's last kernel
     fused_activations = ("relu",)
 
-    def relu_chain_ok(self) -> bool:
+    def relu_chain_ok(self, consumer: bool = True) -> bool:
         """True when this layer can take part in the ReLU-mask delegation of ``forward(..., input_is_relu= / premasked=)``:
-        library convolution, channel counts that need no padding."""
-        return self._conv is conv_cheb and _pad4(self.in_channels) == 0 and _pad4(self.out_channels) == 0
+        library convolution whose output (producer, ``premasked``) — and, for the masking consumer (``input_is_relu``),
+        input as well — needs no channel padding."""
+        return (self._conv is conv_cheb and _pad4(self.out_channels) == 0
+                and (not consumer or _pad4(self.in_channels) == 0))
 
     def forward(self, inputs, activation=None, input_is_relu=False, premasked=False):
         """``forward(inputs)`` is the reference's signature; ``activation="relu"`` (an extension used by

@@ -78,11 +78,11 @@ class ConvBlock(torch.nn.Module):
     def _bn(self, x):
         return self.bn(x.permute(0, 2, 1)).permute(0, 2, 1)
 
-    def relu_chain_ok(self) -> bool:
+    def relu_chain_ok(self, consumer: bool = True) -> bool:
         """This block is a library convolution (+ fused ReLU) and nothing else, on aligned channel counts: it can take
         part in the ReLU-mask delegation (``layers.ConvCheb.forward``)."""
         ok = getattr(self.conv, "relu_chain_ok", None)
-        return bool(ok and ok() and not self.norm and (self._fused_act == "relu" or not self.act))
+        return bool(ok and ok(consumer) and not self.norm and (self._fused_act == "relu" or not self.act))
 
     def forward(self, x, input_is_relu=False, premasked=False):
         if input_is_relu or premasked:  # (only requested by ResBlock after relu_chain_ok())
@@ -143,7 +143,8 @@ class ResBlock(torch.nn.Module):
         relu_in = False
         for i, blk in enumerate(blocks):
             delegate = (_FUSED_SKIPS and i + 1 < len(blocks) and torch.is_grad_enabled()
-                        and getattr(blk, "_fused_act", None) == "relu" and blk.relu_chain_ok() and blocks[i + 1].relu_chain_ok())
+                        and getattr(blk, "_fused_act", None) == "relu" and blk.relu_chain_ok(consumer=relu_in)
+                        and blocks[i + 1].relu_chain_ok())
             if relu_in or delegate:
                 out = blk(out, input_is_relu=relu_in, premasked=delegate)
             else:

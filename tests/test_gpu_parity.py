@@ -1116,6 +1116,8 @@ def test_relu_mask_delegated_to_the_next_layer_matches_threshold_pass(F0, F1, F2
             res.append([y.detach(), xi.grad] + [p.grad.clone() for p in list(c1.parameters()) + list(c2.parameters())])
     finally:
         lib.dsw_set_option(5, 0)
+    # (the masked last Clenshaw hop runs on the row-block SpMM kernel, the unmasked one on the team kernel: same terms,
+    #  another summation order — a few fp32 ulps through the recurrence, not bit-identical)
     for a, b in zip(*res):
-        assert rel_err(b, a) < 1e-6
+        assert rel_err(b, a) < 1e-5
     assert (res[1][1] != 0).any()
