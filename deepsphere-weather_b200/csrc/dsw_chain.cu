@@ -422,9 +422,80 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       if (prof) c1 = clock64();
 
       // Accumulators start at (beta * Z + G) / alpha (alpha is 1 or 2: exact); the loads land while the tile does.
+      // Whole row-blocks of a full 64-channel slab (every item but those of a ragged last tile / last slab) take a
+      // straight-line path: one base address per operand, no per-element range checks — the checked form costs ~600
+      // instructions per item and warp before the entry loop and as many after it, about as many as the loop itself.
+      const bool fast = slab_f == 64 && __all_sync(0xffffffffu, active && blk * 4 + 3 < P.n_rows) && !(P.debug_skip & (8 | 16));
+      const float h_alpha = H.alpha;
       float4 acc[4][4];
-      {
-        const float inv_alpha = 1.f / H.alpha;
+      if (fast) {
+        const float inv_alpha = 1.f / h_alpha;
+        const float zs = H.beta * inv_alpha;
+        const float* const hZ = H.Z;
+        const float* const hG = H.G;
+        const int64_t row0 = (int64_t)blk * 4;
+        if (hZ != nullptr) {
+          const int64_t sv = H.z_sV;
+          const float* zp = hZ + d.b * H.z_sB + row0 * sv + d.slab * 64;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[r][j] = ldcg4(zp + ch[j]);
+            zp += sv;
+          }
+        }
+        if (hG != nullptr) {
+          float4 g[4][4];
+          const int64_t sv = H.g_sV;
+          const float* gp = hG + d.b * H.g_sB + row0 * sv + d.slab * 64;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) g[r][j] = ldcg4(gp + ch[j]);
+            gp += sv;
+          }
+          if (early) {
+            __syncwarp();
+            if (lane == 0) red_release_cta(done, (P.debug_skip & 64) != 0);
+          }
+          if (hZ != nullptr) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                // (same operations as the checked path: round(z * zs), then one fused multiply-add)
+                const float4 z = make_float4(acc[r][j].x * zs, acc[r][j].y * zs, acc[r][j].z * zs, acc[r][j].w * zs);
+                acc[r][j] = make_float4(fmaf(g[r][j].x, inv_alpha, z.x), fmaf(g[r][j].y, inv_alpha, z.y),
+                                        fmaf(g[r][j].z, inv_alpha, z.z), fmaf(g[r][j].w, inv_alpha, z.w));
+              }
+          } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                acc[r][j] = make_float4(fmaf(g[r][j].x, inv_alpha, 0.f), fmaf(g[r][j].y, inv_alpha, 0.f),
+                                        fmaf(g[r][j].z, inv_alpha, 0.f), fmaf(g[r][j].w, inv_alpha, 0.f));
+          }
+        } else {
+          if (early) {
+            __syncwarp();
+            if (lane == 0) red_release_cta(done, (P.debug_skip & 64) != 0);
+          }
+          if (hZ != nullptr) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                acc[r][j] = make_float4(acc[r][j].x * zs, acc[r][j].y * zs, acc[r][j].z * zs, acc[r][j].w * zs);
+          } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      } else {
+        const float inv_alpha = 1.f / h_alpha;
         const float zs = H.beta * inv_alpha;
         bool ok[4][4];
 #pragma unroll
@@ -503,7 +574,29 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       mbar_arrive(bar_empty);
       if (prof) c3 = clock64();
       // ---- epilogue: O = alpha * acc ----
-      if (active && !(P.debug_skip & 8)) {
+      if (fast) {
+        const int64_t sv = H.o_sV;
+        float* op = H.O + d.b * H.o_sB + (int64_t)blk * 4 * sv + d.slab * 64;
+        const float* mp = nullptr;
+        int64_t msv = 0;
+        if (MASK && H.M != nullptr) msv = H.m_sV, mp = H.M + d.b * H.m_sB + (int64_t)blk * 4 * msv + d.slab * 64;
+        const bool relu = H.act != 0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4 o = make_float4(h_alpha * acc[r][j].x, h_alpha * acc[r][j].y, h_alpha * acc[r][j].z, h_alpha * acc[r][j].w);
+            if (relu) o.x = fmaxf(o.x, 0.f), o.y = fmaxf(o.y, 0.f), o.z = fmaxf(o.z, 0.f), o.w = fmaxf(o.w, 0.f);
+            if (MASK && mp != nullptr) {  // ReLU mask of a gradient by the ReLU's output (indexed like the output rows)
+              const float4 m = ldcg4(mp + ch[j]);
+              o.x = m.x > 0.f ? o.x : 0.f, o.y = m.y > 0.f ? o.y : 0.f, o.z = m.z > 0.f ? o.z : 0.f, o.w = m.w > 0.f ? o.w : 0.f;
+            }
+            *reinterpret_cast<float4*>(op + ch[j]) = o;
+          }
+          op += sv;
+          if (MASK) mp += msv;
+        }
+      } else if (active && !(P.debug_skip & 8)) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           const int row = blk * 4 + r;

@@ -604,38 +604,43 @@ __global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
     {
       const float inv_alpha = 1.f / a.alpha;
       const float zs = a.beta * inv_alpha;
-      bool ok[4][NJ];
-      int64_t eoff[4][NJ];
+      // No per-element range checks here: rows past the end (or of an inactive row-block) and channels past the slab are
+      // CLAMPED to valid addresses — their accumulators are computed on junk and never stored.  (The checked form cost
+      // several hundred instructions per item and warp.)
+      int chc[NJ];
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+      for (int j = 0; j < NJ; ++j) chc[j] = slab * 64 + min(ch[j], slab_f - 4);
+      int64_t rowc[4];
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          ok[r][j] = orow[r] >= 0 && ch[j] < slab_f;
-          eoff[r][j] = (int64_t)slab * 64 + ch[j];
-        }
+      for (int r = 0; r < 4; ++r) rowc[r] = PERM ? max(orow[r], 0) : min(blk * 4 + r, P.n_rows - 1);
       // batch 1: all Z loads in flight together
+      if (a.Z != nullptr) {
+        const float* zb = a.Z + b * a.z_sB;
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < 4; ++r) {
+          const float* zr = zb + rowc[r] * a.z_sV;
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          acc[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (a.Z != nullptr && ok[r][j]) acc[r][j] = ldcg4(a.Z + b * a.z_sB + (int64_t)orow[r] * a.z_sV + eoff[r][j]);
+          for (int j = 0; j < NJ; ++j) {
+            const float4 z = ldcg4(zr + chc[j]);
+            acc[r][j] = make_float4(z.x * zs, z.y * zs, z.z * zs, z.w * zs);
+          }
         }
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int j = 0; j < NJ; ++j)
-          acc[r][j] = make_float4(acc[r][j].x * zs, acc[r][j].y * zs, acc[r][j].z * zs, acc[r][j].w * zs);
-      // batch 2 (adjoint recurrence only): all G loads in flight together
-      if (a.G != nullptr) {
-        float4 g[4][NJ];
+      } else {
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-          for (int j = 0; j < NJ; ++j) {
-            g[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (ok[r][j]) g[r][j] = ldcg4(a.G + b * a.g_sB + (int64_t)orow[r] * a.g_sV + eoff[r][j]);
-          }
+          for (int j = 0; j < NJ; ++j) acc[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      // batch 2 (adjoint recurrence only): all G loads in flight together
+      if (a.G != nullptr) {
+        float4 g[4][NJ];
+        const float* gb = a.G + b * a.g_sB;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float* gr = gb + rowc[r] * a.g_sV;
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) g[r][j] = ldcg4(gr + chc[j]);
+        }
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
