@@ -124,6 +124,26 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+// L2 eviction hints: a Z row is read for the last time by this launch, and the last hop's output is not read by it at all —
+// both leave the L2 first, which keeps the planes the next hop pass still needs resident.
+__device__ __forceinline__ uint64_t l2_policy(bool evict_first) {
+  uint64_t p;
+  if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ldcg4_hint(const float* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void st4_hint(float* p, const float4& v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol)
+               : "memory");
+}
 __device__ __forceinline__ void fma4(float4& acc, float w, const float4& x) {
   const float2 ww = make_float2(w, w);
   float2 lo = __ffma2_rn(ww, make_float2(x.x, x.y), make_float2(acc.x, acc.y));
@@ -344,6 +364,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         d.idx = idx, d.hop = hop, d.tile = tile, d.b = b, d.slab = slab;
         s_item[team * CH_DESC_RING + (n % CH_DESC_RING)] = d;
         mbar_expect_tx(bar_full, (uint32_t)tm.z * 256u + (uint32_t)tm.y * (DSW_TILE_BLOCKS * 20u));
+        // `ready` goes out BEFORE the ~24 transfer instructions (~1.4 k cycles of issue): the team reads the descriptor and
+        // sends its Z / G loads while the boxes are still being issued, then waits on `full`
+        mbar_arrive(bar_ready);
         bulk_g2s(sval_u32, P.tp_val + (size_t)tm.x * DSW_TILE_BLOCKS, (uint32_t)tm.y * (DSW_TILE_BLOCKS * 16u), bar_full);
         bulk_g2s(soff_u32, P.tp_off + (size_t)tm.x * DSW_TILE_BLOCKS, (uint32_t)tm.y * (DSW_TILE_BLOCKS * 4u), bar_full);
       }
@@ -356,7 +379,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         tma_load_3d(xs_u32 + ((uint32_t)pc.x >> 8) * 256u, mp + (pc.x & 7), slab * 64, pc.y, b, bar_full);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_ready);
       if (cprof && n > 0) {
         k3 = clock64();
         atomicAdd(&g_chain_prof[8], (unsigned long long)(k1 - k0));   // claim, decode, metadata, early dependency look
@@ -390,6 +412,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     const float4* pw = s_val + slot;
     int ch[4];
     ch[0] = (int)(cA >> 2), ch[1] = (int)(cB >> 2), ch[2] = ch[0] + 32, ch[3] = ch[1] + 32;
+
+    const uint64_t pol_normal = l2_policy(false);
+    const uint64_t pol_first = l2_policy(true);
 
     for (uint32_t n = 0;; ++n) {
       const bool prof = (P.debug_skip & 4) && (tt == 0);
@@ -440,7 +465,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[r][j] = ldcg4(zp + ch[j]);
+            for (int j = 0; j < 4; ++j) acc[r][j] = ldcg4_hint(zp + ch[j], pol_first);
             zp += sv;
           }
         }
@@ -451,7 +476,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) g[r][j] = ldcg4(gp + ch[j]);
+            for (int j = 0; j < 4; ++j) g[r][j] = ldcg4_hint(gp + ch[j], pol_first);
             gp += sv;
           }
           if (early) {
@@ -581,6 +606,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         int64_t msv = 0;
         if (MASK && H.M != nullptr) msv = H.m_sV, mp = H.M + d.b * H.m_sB + (int64_t)blk * 4 * msv + d.slab * 64;
         const bool relu = H.act != 0;
+        const uint64_t pol_out = d.hop == P.n_hops - 1 ? pol_first : pol_normal;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
 #pragma unroll
@@ -591,7 +617,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
               const float4 m = ldcg4(mp + ch[j]);
               o.x = m.x > 0.f ? o.x : 0.f, o.y = m.y > 0.f ? o.y : 0.f, o.z = m.z > 0.f ? o.z : 0.f, o.w = m.w > 0.f ? o.w : 0.f;
             }
-            *reinterpret_cast<float4*>(op + ch[j]) = o;
+            st4_hint(op + ch[j], o, pol_out);
           }
           op += sv;
           if (MASK) mp += msv;
