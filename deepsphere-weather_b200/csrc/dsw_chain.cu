@@ -164,7 +164,8 @@ __device__ __forceinline__ void fma_step(float4 (&acc)[4][4], const float4& w, c
 struct ItemDesc {
   int32_t idx;   // claim index (< 0: nothing left, leave)
   int32_t hop, tile, b, slab;
-  int32_t pad[3];
+  int32_t wlen[2];  // entry-loop trip count of the team's first / second warp (plan: tile_meta)
+  int32_t pad;
 };
 
 // mbarriers of one team
@@ -326,6 +327,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       const int32_t b = g * P.S + s;
       // one round trip: tile record, this lane's pieces, this lane's dependency
       const int4 tm = __ldg(P.tile_meta + 2 * tile);  // {panel step offset, steps, source rows, pieces}
+      const int4 tm2 = __ldg(P.tile_meta + 2 * tile + 1);  // {deps, trip count of warp 0, of warp 1, -} (same 32-byte sector)
       int2 pc0 = make_int2(-1, 0), pc1 = make_int2(-1, 0);
       if (lane < P.pieces_stride) pc0 = __ldg(P.tpc_fix + (size_t)tile * P.pieces_stride + lane);
       if (lane + 32 < P.pieces_stride) pc1 = __ldg(P.tpc_fix + (size_t)tile * P.pieces_stride + lane + 32);
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       if (lane == 0) {
         ItemDesc d;
-        d.idx = idx, d.hop = hop, d.tile = tile, d.b = b, d.slab = slab;
+        d.idx = idx, d.hop = hop, d.tile = tile, d.b = b, d.slab = slab, d.wlen[0] = tm2.y, d.wlen[1] = tm2.z;
         s_item[team * CH_DESC_RING + (n % CH_DESC_RING)] = d;
         mbar_expect_tx(bar_full, (uint32_t)tm.z * 256u + (uint32_t)tm.y * (DSW_TILE_BLOCKS * 20u));
         // `ready` goes out BEFORE the ~24 transfer instructions (~1.4 k cycles of issue): the team reads the descriptor and
@@ -442,8 +444,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       const int blk = d.tile * DSW_TILE_BLOCKS + slot;
       const bool active = blk < P.n_blocks;
       const int slab_f = min(64, P.F - d.slab * 64);
-      int my_len = 0;
-      if (active) my_len = __ldg(P.blkptr + blk + 1) - __ldg(P.blkptr + blk);
       if (prof) c1 = clock64();
 
       // Accumulators start at (beta * Z + G) / alpha (alpha is 1 or 2: exact); the loads land while the tile does.
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       const float h_alpha = H.alpha;
       float4 acc[4][4];
       if (fast) {
-        const float inv_alpha = 1.f / h_alpha;
+        const float inv_alpha = h_alpha == 2.f ? 0.5f : 1.f;  // (the launcher admits alpha 1 and 2 only)
         const float zs = H.beta * inv_alpha;
         const float* const hZ = H.Z;
         const float* const hG = H.G;
@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
                                       fmaf(g[r][j].z, inv_alpha, acc[r][j].z), fmaf(g[r][j].w, inv_alpha, acc[r][j].w));
         }
       }
-      const int wlen = (__reduce_max_sync(0xffffffffu, my_len) + 1) & ~1;
+      const int wlen = d.wlen[tt >> 5];  // (no global load on the team's path: it used to delay the Z / G loads by an L2 round trip)
       mbar_wait(bar_full, n & 1u);
       if (prof) c2 = clock64();
 

@@ -66,7 +66,7 @@ struct dsw_rb {
   int32_t* tdep_ptr = nullptr;   // [n_tiles + 1]
   int32_t* tdep_idx = nullptr;
   // the same per-tile metadata at fixed strides, so that the chain kernel's issuer warp fetches all of it in one round trip
-  int4* tile_meta = nullptr;     // [n_tiles][2]: {panel step offset, steps incl. pad, source rows, pieces}, {deps, 0, 0, 0}
+  int4* tile_meta = nullptr;     // [n_tiles][2]: {panel step offset, steps incl. pad, source rows, pieces}, {deps, entry-loop steps of compute warp 0, of warp 1, 0}
   int2* tpc_fix = nullptr;       // [n_tiles][tile_pieces_max]: {meta, first source row}; meta = 0xffffffff past the tile's pieces
   int32_t* tdep_fix = nullptr;   // [n_tiles][tile_deps_max], -1 past the tile's dependencies
   int32_t chain_flag_cap = 0;

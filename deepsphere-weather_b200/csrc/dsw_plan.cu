@@ -441,7 +441,14 @@ static cudaError_t upload_rb(dsw_rb* d, const HostRb& h, cudaStream_t st, bool s
         for (int32_t t = 0; t < h.n_tiles; ++t) {
           const int32_t np = h.tpc_ptr[t + 1] - h.tpc_ptr[t], nd = h.tdep_ptr[t + 1] - h.tdep_ptr[t];
           meta[2 * t] = make_int4(h.tp_ptr[t], h.tp_ptr[t + 1] - h.tp_ptr[t], h.tile_ptr[t + 1] - h.tile_ptr[t], np);
-          meta[2 * t + 1] = make_int4(nd, 0, 0, 0);
+          // entry-loop trip counts of the tile's two compute warps (row-block slots 0-7 / 8-15): longest union, rounded up
+          // to the two-step software pipeline — handed to the team through the item descriptor
+          int32_t wl[2] = {0, 0};
+          for (int32_t sl = 0; sl < DSW_TILE_BLOCKS; ++sl) {
+            const int32_t blk = t * DSW_TILE_BLOCKS + sl;
+            if (blk < h.n_blocks) wl[sl / (DSW_TILE_BLOCKS / 2)] = std::max(wl[sl / (DSW_TILE_BLOCKS / 2)], h.blkptr[blk + 1] - h.blkptr[blk]);
+          }
+          meta[2 * t + 1] = make_int4(nd, (wl[0] + 1) & ~1, (wl[1] + 1) & ~1, 0);
           for (int32_t i = 0; i < np; ++i)
             pcs[static_cast<size_t>(t) * h.tile_pieces_max + i] =
                 make_int2(static_cast<int32_t>(h.tpc_meta[h.tpc_ptr[t] + i]), h.tpc_row[h.tpc_ptr[t] + i]);
