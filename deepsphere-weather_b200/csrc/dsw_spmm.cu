@@ -494,14 +494,15 @@ __global__ void __launch_bounds__(DSW_TILE_BLOCKS* LPR* MAX_TEAMS, 1)
     } else if (TMA) {
       // one lane issues a tensor-map box per piece (run of consecutive source rows); the copies bypass
       // registers and L1, complete on the team's mbarrier, and out-of-range channels are zero-filled
-      if (tt < 32) {
+      {
+        // The boxes are dealt round-robin over the team's warps: a TMA instruction costs ~60 cycles of issue from one
+        // warp, and the issuing warps are compute warps — one warp issuing all ~24 boxes ran 1.4 k cycles behind its peer
+        // on every item.  (The phase cannot complete before lane 0's expect_tx arrival, so boxes may be issued ahead of it.)
+        constexpr int NW = TEAM_THREADS / 32;
         const uint32_t bar = hop_smem_u32(s_bar + team);
-        if (tt == 0) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          hop_mbar_expect_tx(bar, (uint32_t)nrows * 256u);
-        }
-        __syncwarp();
-        for (int i = tt; i < npieces; i += 32) {  // the lanes of the first warp issue the boxes in parallel
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (tt == 0) hop_mbar_expect_tx(bar, (uint32_t)nrows * 256u);
+        for (int i = (tt & 31) * NW + (tt >> 5); i < npieces; i += 32 * NW) {
           const uint32_t meta = s_meta[i];
           tma_load_3d(xs_u32 + (meta >> 8) * 256u, &maps.m[meta & 7u], slab * 64, s_row[i], b, bar);
         }
