@@ -160,6 +160,16 @@ __device__ __forceinline__ void fma_step(float4 (&acc)[4][4], const float4& w, c
   }
 }
 
+__device__ __forceinline__ void fma_step2(float4 (&acc)[4][4], const float4& w, const float4 (&x)[2]) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    fma4(acc[0][j], w.x, x[j]);
+    fma4(acc[1][j], w.y, x[j]);
+    fma4(acc[2][j], w.z, x[j]);
+    fma4(acc[3][j], w.w, x[j]);
+  }
+}
+
 // What a team needs to know about its current item (written by its issuer warp, read after the `ready` barrier).
 struct ItemDesc {
   int32_t idx;   // claim index (< 0: nothing left, leave)
@@ -565,11 +575,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
                                       fmaf(g[r][j].z, inv_alpha, acc[r][j].z), fmaf(g[r][j].w, inv_alpha, acc[r][j].w));
         }
       }
-      const int wlen = d.wlen[tt >> 5];  // (no global load on the team's path: it used to delay the Z / G loads by an L2 round trip)
+      const int wlen = (tt >> 5) ? d.wlen[1] : d.wlen[0];  // (no global load on the team's path: it used to delay the Z / G loads by an L2 round trip)
       mbar_wait(bar_full, n & 1u);
       if (prof) c2 = clock64();
 
-      {
+      if (slab_f > 32) {
         auto load_x = [&](uint32_t o, float4(&x)[4]) {
           x[0] = *reinterpret_cast<const float4*>(xA + o);
           x[1] = *reinterpret_cast<const float4*>(xB + o);
@@ -592,6 +602,29 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
           load_x(o2, x0);
           o1 = po[(u + 3) * DSW_TILE_BLOCKS];
           fma_step(acc, w1, x1);
+        }
+      } else {
+        // a slab of at most 32 channels (24-channel first layer, narrow last slabs): accumulator columns 2 and 3 (channels
+        // 32-63) are never stored — half the shared-memory reads and FMAs
+        auto load_x2 = [&](uint32_t o, float4(&x)[2]) {
+          x[0] = *reinterpret_cast<const float4*>(xA + o);
+          x[1] = *reinterpret_cast<const float4*>(xB + o);
+        };
+        float4 x0[2], x1[2], w0, w1;
+        uint32_t o1, o2;
+        w0 = pw[0];
+        load_x2(po[0], x0);
+        o1 = po[DSW_TILE_BLOCKS];
+#pragma unroll 1
+        for (int u = 0; u < ((P.debug_skip & 2) ? 0 : wlen); u += 2) {
+          w1 = pw[(u + 1) * DSW_TILE_BLOCKS];
+          load_x2(o1, x1);
+          o2 = po[(u + 2) * DSW_TILE_BLOCKS];
+          fma_step2(acc, w0, x0);
+          w0 = pw[(u + 2) * DSW_TILE_BLOCKS];
+          load_x2(o2, x0);
+          o1 = po[(u + 3) * DSW_TILE_BLOCKS];
+          fma_step2(acc, w1, x1);
         }
       }
       // this lane is done with the staged rows and panels (every lane arrives itself: its own shared-memory reads are
