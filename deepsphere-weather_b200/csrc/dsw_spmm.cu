@@ -106,6 +106,58 @@ __global__ void __launch_bounds__(512) hop_rb_kernel(const int32_t* __restrict__
   }
 }
 
+// Four-channel planes (the 2-channel output head padded to 4, its gradient): one lane owns a row for NB samples, so the
+// row's column / weight list — read uncoalesced, lane by lane — is fetched once per NB samples instead of once per sample
+// (the plain CSR kernel below was bound by exactly those sector loads: 34 us per hop on 12 288 nodes x 32 samples).
+// Same operation order per output element as hop_csr_kernel (results are bit-identical).
+template <int NB>
+__global__ void __launch_bounds__(256) hop_csr_f4_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                         const float* __restrict__ val, int32_t n_rows, HopArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  const int row = blockIdx.x * 256 + threadIdx.x;
+  const int b0 = blockIdx.y * NB;
+  if (row >= n_rows) return;
+  const int e0 = __ldg(rowptr + row), e1 = __ldg(rowptr + row + 1);
+  const int nb = min(NB, a.B - b0);
+  const float* __restrict__ xb = a.X + (int64_t)b0 * a.x_sB;
+  float4 acc[NB];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int e = e0; e < e1; ++e) {
+    const int c = __ldg(col + e);
+    const float w = __ldg(val + e);
+    float4 x[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) x[i] = i < nb ? ldg4(xb + i * a.x_sB + c * a.x_sV) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      acc[i].x = fmaf(w, x[i].x, acc[i].x), acc[i].y = fmaf(w, x[i].y, acc[i].y);
+      acc[i].z = fmaf(w, x[i].z, acc[i].z), acc[i].w = fmaf(w, x[i].w, acc[i].w);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    if (i >= nb) break;
+    const int64_t b = b0 + i;
+    float o[4] = {a.alpha * acc[i].x, a.alpha * acc[i].y, a.alpha * acc[i].z, a.alpha * acc[i].w};
+    if (a.Z) {
+      const float4 z = ldg4(a.Z + b * a.z_sB + row * a.z_sV);
+      o[0] = fmaf(a.beta, z.x, o[0]), o[1] = fmaf(a.beta, z.y, o[1]), o[2] = fmaf(a.beta, z.z, o[2]), o[3] = fmaf(a.beta, z.w, o[3]);
+    }
+    if (a.G) {
+      const float4 g = ldg4(a.G + b * a.g_sB + row * a.g_sV);
+      o[0] += g.x, o[1] += g.y, o[2] += g.z, o[3] += g.w;
+    }
+    if (a.act) o[0] = fmaxf(o[0], 0.f), o[1] = fmaxf(o[1], 0.f), o[2] = fmaxf(o[2], 0.f), o[3] = fmaxf(o[3], 0.f);
+    if (a.M) {
+      const float4 m = ldg4(a.M + b * a.m_sB + row * a.m_sV);
+      o[0] = m.x > 0.f ? o[0] : 0.f, o[1] = m.y > 0.f ? o[1] : 0.f, o[2] = m.z > 0.f ? o[2] : 0.f, o[3] = m.w > 0.f ? o[3] : 0.f;
+    }
+    *reinterpret_cast<float4*>(a.O + b * a.o_sB + row * a.o_sV) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // Plain CSR.  LPR (power of two) lanes cooperate on one row; each lane walks columns
 // c = lane, lane + LPR, ... in units of VEC floats.
 template <int VEC>
@@ -129,6 +181,24 @@ __global__ void __launch_bounds__(256) hop_csr_kernel(const int32_t* __restrict_
 #pragma unroll
     for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
     int e = e0;
+    // eight entries per trip: all column / weight loads, then all gathers, are in flight together (the 2-entry form below
+    // kept two gathers in flight per lane: latency-bound on narrow planes); the FMAs keep the entry order
+    if constexpr (VEC == 4) {
+      for (; e + 8 <= e1; e += 8) {
+        int c[8];
+        float w[8];
+        float4 xv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c[i] = __ldg(col + e + i), w[i] = __ldg(val + e + i);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xv[i] = ldg4(xb + c[i] * a.x_sV + f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[0] = fmaf(w[i], xv[i].x, acc[0]), acc[1] = fmaf(w[i], xv[i].y, acc[1]);
+          acc[2] = fmaf(w[i], xv[i].z, acc[2]), acc[3] = fmaf(w[i], xv[i].w, acc[3]);
+        }
+      }
+    }
     for (; e + 2 <= e1; e += 2) {
       const int ca = __ldg(col + e), cb = __ldg(col + e + 1);
       const float wa = __ldg(val + e), wb = __ldg(val + e + 1);
@@ -877,6 +947,13 @@ int launch_hop(const dsw_csr& A, const dsw_rb& rb, const HopArgs& a, cudaStream_
       hop_rb_kernel<4><<<grid, threads, 0, st>>>(rb.blkptr, rb.ucol, rb.uval, rb.n_blocks, A.n_rows, a);
     else
       hop_rb_kernel<2><<<grid, threads, 0, st>>>(rb.blkptr, rb.ucol, rb.uval, rb.n_blocks, A.n_rows, a);
+    return check_launch();
+  }
+  if (v4 && a.F == 4 && a.B >= 8) {
+    constexpr int NB = 8;
+    dim3 grid(ceil_div(A.n_rows, 256), ceil_div(a.B, NB));
+    DSW_CUDA_TRY(launch_pdl(hop_csr_f4_kernel<NB>, grid, dim3(256), 0, st, pdl_enabled(), (const int32_t*)A.rowptr,
+                            (const int32_t*)A.col, (const float*)A.val, (int32_t)A.n_rows, a));
     return check_launch();
   }
   const int vec = v4 ? 4 : 1;

@@ -38,6 +38,8 @@ def _terms_ref_cpu(lap, x, K):
     (16, 4, 64, 4),
     (8, 2, 512, 3),     # 8 slabs
     (2, 3, 16, 4),      # one partial tile (48 rows)
+    (8, 4, 24, 4),      # the 24-channel first layer: half-width entry loop, checked accumulator init / stores
+    (8, 2, 32, 3),      # a whole slab of exactly 32 channels
     (8, 4, 64, 9),      # 8 hops: two chain launches (DSW_CHAIN_MAX_HOPS = 7)
 ])
 @pytest.mark.parametrize("group", ["default", "one-sample-groups", "ragged-groups"])

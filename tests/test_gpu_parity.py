@@ -215,13 +215,19 @@ def _flat_storage(t):
     return torch.as_strided(t, (n,), (1,), 0)
 
 
-def test_cheb_terms_match_oracle_recurrence(dev):
+@pytest.mark.parametrize("B,F", [(2, 64), (11, 4), (16, 4), (3, 4), (5, 24), (4, 32), (2, 96)],
+                         ids=["b2-f64", "b11-f4-ragged-sample-groups", "b16-f4", "b3-f4-plain-csr", "b5-f24-narrow-slab",
+                              "b4-f32-narrow-slab", "b2-f96-ragged-last-slab"])
+def test_cheb_terms_match_oracle_recurrence(B, F, dev):
+    """dsw_cheb_terms against the recurrence of layers.py:163-169 on torch-CPU sparse products, over the channel widths that
+    pick different hop kernels: 64-channel slabs, the 4-channel multi-sample CSR kernel (whole and ragged groups of 8
+    samples; fewer than 8 samples: plain CSR), slabs of <= 32 channels (half-width entry loop), a ragged last slab."""
     from deepsphere_weather_b200 import functional as F_
     from deepsphere_weather_b200 import graphs as G
 
     torch.manual_seed(1)
     lap = G.healpix_laplacian(4)
-    x = torch.randn(2, 192, 64)
+    x = torch.randn(B, 192, F)
     got = F_.cheb_terms(x.to(dev), F_.plan_for(lap.to(dev)), 5).cpu()
     flat = x.permute(1, 2, 0).reshape(192, -1)
     t0, t1 = flat, torch.sparse.mm(lap, flat)
@@ -230,7 +236,7 @@ def test_cheb_terms_match_oracle_recurrence(dev):
         t0, t1 = t1, 2 * torch.sparse.mm(lap, t1) - t0
         terms.append(t1)
     for k, t in enumerate(terms):
-        want = t.reshape(192, 64, 2).permute(2, 0, 1)
+        want = t.reshape(192, F, B).permute(2, 0, 1)
         assert rel_err(got[k], want) < 1e-5, k
 
 
