@@ -175,13 +175,14 @@ struct ItemDesc {
   int32_t idx;   // claim index (< 0: nothing left, leave)
   int32_t hop, tile, b, slab;
   int32_t wlen[2];  // entry-loop trip count of the team's first / second warp (plan: tile_meta)
-  int32_t pad;
+  int32_t split;    // plan: tile_split (pieces of group A | rows of A << 8 | steps on A only, warp 0 << 16 | warp 1 << 24)
 };
 
 // mbarriers of one team
 struct TeamBars {
   uint64_t ready;  // issuer -> team: descriptor written, dependencies met, transfers issued (count 1)
-  uint64_t full;   // transfers -> team: rows and panels have landed (count 1 + tx bytes)
+  uint64_t full;   // transfers -> team: the panels and the rows of group A have landed (count 1 + tx bytes)
+  uint64_t full2;  // transfers -> team: the other rows have landed (count 1 + tx bytes)
   uint64_t empty;  // team -> issuer: the entry loop is over, the buffers may be overwritten (count 64: every lane)
 };
 
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
   if (tid < CH_TEAMS) {
     mbar_init(smem_u32(&s_bars[tid].ready), 1);
     mbar_init(smem_u32(&s_bars[tid].full), 1);
+    mbar_init(smem_u32(&s_bars[tid].full2), 1);
     mbar_init(smem_u32(&s_bars[tid].empty), CH_TEAM_THREADS);
     s_words[tid].done[0] = 0, s_words[tid].done[1] = 0, s_words[tid].published = 0, s_words[tid].total = -1;
   }
@@ -298,6 +300,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     const uint32_t sval_u32 = xs_u32 + (uint32_t)P.cap_rows * 256u;
     const uint32_t soff_u32 = sval_u32 + (uint32_t)(P.cap_len + DSW_PANEL_PAD) * DSW_TILE_BLOCKS * 16u;
     const uint32_t bar_ready = smem_u32(&s_bars[team].ready), bar_full = smem_u32(&s_bars[team].full);
+    const uint32_t bar_full2 = smem_u32(&s_bars[team].full2);
     const uint32_t bar_empty = smem_u32(&s_bars[team].empty);
     const bool cprof = (P.debug_skip & 4) && (lane == 0);
 
@@ -337,7 +340,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       const int32_t b = g * P.S + s;
       // one round trip: tile record, this lane's pieces, this lane's dependency
       const int4 tm = __ldg(P.tile_meta + 2 * tile);  // {panel step offset, steps, source rows, pieces}
-      const int4 tm2 = __ldg(P.tile_meta + 2 * tile + 1);  // {deps, trip count of warp 0, of warp 1, -} (same 32-byte sector)
+      const int4 tm2 = __ldg(P.tile_meta + 2 * tile + 1);  // {deps, trip count of warp 0, of warp 1, split} (same 32-byte sector)
+      const int32_t split = (P.debug_skip & 4096) ? 0 : tm2.w;
+      const int n_a = split & 0xff;
+      const uint32_t rows_a = ((uint32_t)split >> 8) & 0xffu;
       int2 pc0 = make_int2(-1, 0), pc1 = make_int2(-1, 0);
       if (lane < P.pieces_stride) pc0 = __ldg(P.tpc_fix + (size_t)tile * P.pieces_stride + lane);
       if (lane + 32 < P.pieces_stride) pc1 = __ldg(P.tpc_fix + (size_t)tile * P.pieces_stride + lane + 32);
@@ -373,9 +379,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       if (lane == 0) {
         ItemDesc d;
-        d.idx = idx, d.hop = hop, d.tile = tile, d.b = b, d.slab = slab, d.wlen[0] = tm2.y, d.wlen[1] = tm2.z;
+        d.idx = idx, d.hop = hop, d.tile = tile, d.b = b, d.slab = slab, d.wlen[0] = tm2.y, d.wlen[1] = tm2.z, d.split = split;
         s_item[team * CH_DESC_RING + (n % CH_DESC_RING)] = d;
-        mbar_expect_tx(bar_full, (uint32_t)tm.z * 256u + (uint32_t)tm.y * (DSW_TILE_BLOCKS * 20u));
+        // two phases: the panels + the rows of group A (the run that holds the tile's own rows: 2-3 boxes), then the rest
+        mbar_expect_tx(bar_full, rows_a * 256u + (uint32_t)tm.y * (DSW_TILE_BLOCKS * 20u));
+        mbar_expect_tx(bar_full2, ((uint32_t)tm.z - rows_a) * 256u);
         // `ready` goes out BEFORE the ~24 transfer instructions (~1.4 k cycles of issue): the team reads the descriptor and
         // sends its Z / G loads while the boxes are still being issued, then waits on `full`
         mbar_arrive(bar_ready);
@@ -384,11 +392,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
       }
       __syncwarp();
       const CUtensorMap* mp = &maps.m[hop][0];
-      if (pc0.x != -1) tma_load_3d(xs_u32 + ((uint32_t)pc0.x >> 8) * 256u, mp + (pc0.x & 7), slab * 64, pc0.y, b, bar_full);
-      if (pc1.x != -1) tma_load_3d(xs_u32 + ((uint32_t)pc1.x >> 8) * 256u, mp + (pc1.x & 7), slab * 64, pc1.y, b, bar_full);
+      // (the pieces of group A are the first n_a of the tile's list: lanes 0 .. n_a - 1 issue them first)
+      if (pc0.x != -1)
+        tma_load_3d(xs_u32 + ((uint32_t)pc0.x >> 8) * 256u, mp + (pc0.x & 7), slab * 64, pc0.y, b, lane < n_a ? bar_full : bar_full2);
+      if (pc1.x != -1)
+        tma_load_3d(xs_u32 + ((uint32_t)pc1.x >> 8) * 256u, mp + (pc1.x & 7), slab * 64, pc1.y, b, lane + 32 < n_a ? bar_full : bar_full2);
       for (int i = lane + 64; i < tm.w; i += 32) {
         const int2 pc = __ldg(P.tpc_fix + (size_t)tile * P.pieces_stride + i);
-        tma_load_3d(xs_u32 + ((uint32_t)pc.x >> 8) * 256u, mp + (pc.x & 7), slab * 64, pc.y, b, bar_full);
+        tma_load_3d(xs_u32 + ((uint32_t)pc.x >> 8) * 256u, mp + (pc.x & 7), slab * 64, pc.y, b, i < n_a ? bar_full : bar_full2);
       }
       __syncwarp();
       if (cprof && n > 0) {
@@ -413,6 +424,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
     const uint32_t* s_off =
         reinterpret_cast<const uint32_t*>(xs + (size_t)P.cap_rows * 256 + (size_t)(P.cap_len + DSW_PANEL_PAD) * DSW_TILE_BLOCKS * 16);
     const uint32_t bar_ready = smem_u32(&s_bars[team].ready), bar_full = smem_u32(&s_bars[team].full);
+    const uint32_t bar_full2 = smem_u32(&s_bars[team].full2);
     const uint32_t bar_empty = smem_u32(&s_bars[team].empty);
     uint32_t* const done = &s_words[team].done[tt >> 5];
     const int slot = tt >> 2, lq = tt & 3, par = slot & 1;
@@ -576,8 +588,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
         }
       }
       const int wlen = (tt >> 5) ? d.wlen[1] : d.wlen[0];  // (no global load on the team's path: it used to delay the Z / G loads by an L2 round trip)
-      mbar_wait(bar_full, n & 1u);
-      if (prof) c2 = clock64();
+      // entry steps [0, wsplit) gather from group A only (the run of rows that holds the tile's own rows: it lands first, with
+      // the panels); the loop runs them while the other boxes are still being issued / in flight, then waits for `full2`
+      const int wsplit = min(wlen, (int)(((uint32_t)d.split >> ((tt >> 5) ? 24 : 16)) & 0xffu));
+      const int n_steps = (P.debug_skip & 2) ? 0 : wlen;
 
       if (slab_f > 32) {
         auto load_x = [&](uint32_t o, float4(&x)[4]) {
@@ -586,22 +600,30 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
           x[2] = *reinterpret_cast<const float4*>(xA + o + 128);
           x[3] = *reinterpret_cast<const float4*>(xB + o + 128);
         };
-        // software pipeline: offsets two steps ahead, weights / values one step ahead (the panels end in zero steps)
-        float4 x0[4], x1[4], w0, w1;
-        uint32_t o1, o2;
-        w0 = pw[0];
-        load_x(po[0], x0);
-        o1 = po[DSW_TILE_BLOCKS];
 #pragma unroll 1
-        for (int u = 0; u < ((P.debug_skip & 2) ? 0 : wlen); u += 2) {
-          w1 = pw[(u + 1) * DSW_TILE_BLOCKS];
-          load_x(o1, x1);
-          o2 = po[(u + 2) * DSW_TILE_BLOCKS];
-          fma_step(acc, w0, x0);
-          w0 = pw[(u + 2) * DSW_TILE_BLOCKS];
-          load_x(o2, x0);
-          o1 = po[(u + 3) * DSW_TILE_BLOCKS];
-          fma_step(acc, w1, x1);
+        for (int seg = 0; seg < 2; ++seg) {
+          mbar_wait(seg ? bar_full2 : bar_full, n & 1u);
+          if (prof && seg == 0) c2 = clock64();
+          const int u0 = seg ? wsplit : 0, u1 = seg ? n_steps : min(wsplit, n_steps);
+          if (u0 >= u1) continue;
+          // software pipeline: offsets two steps ahead, weights / values one step ahead (the panels end in zero steps; what
+          // the last trip of the first segment reads ahead may not have landed yet and is discarded)
+          float4 x0[4], x1[4], w0, w1;
+          uint32_t o1, o2;
+          w0 = pw[u0 * DSW_TILE_BLOCKS];
+          load_x(po[u0 * DSW_TILE_BLOCKS], x0);
+          o1 = po[(u0 + 1) * DSW_TILE_BLOCKS];
+#pragma unroll 1
+          for (int u = u0; u < u1; u += 2) {
+            w1 = pw[(u + 1) * DSW_TILE_BLOCKS];
+            load_x(o1, x1);
+            o2 = po[(u + 2) * DSW_TILE_BLOCKS];
+            fma_step(acc, w0, x0);
+            w0 = pw[(u + 2) * DSW_TILE_BLOCKS];
+            load_x(o2, x0);
+            o1 = po[(u + 3) * DSW_TILE_BLOCKS];
+            fma_step(acc, w1, x1);
+          }
         }
       } else {
         // a slab of at most 32 channels (24-channel first layer, narrow last slabs): accumulator columns 2 and 3 (channels
@@ -610,13 +632,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
           x[0] = *reinterpret_cast<const float4*>(xA + o);
           x[1] = *reinterpret_cast<const float4*>(xB + o);
         };
+        mbar_wait(bar_full, n & 1u);
+        mbar_wait(bar_full2, n & 1u);
+        if (prof) c2 = clock64();
         float4 x0[2], x1[2], w0, w1;
         uint32_t o1, o2;
         w0 = pw[0];
         load_x2(po[0], x0);
         o1 = po[DSW_TILE_BLOCKS];
 #pragma unroll 1
-        for (int u = 0; u < ((P.debug_skip & 2) ? 0 : wlen); u += 2) {
+        for (int u = 0; u < n_steps; u += 2) {
           w1 = pw[(u + 1) * DSW_TILE_BLOCKS];
           load_x2(o1, x1);
           o2 = po[(u + 2) * DSW_TILE_BLOCKS];

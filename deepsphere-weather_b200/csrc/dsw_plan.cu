@@ -3,6 +3,8 @@
 // Replaces the COO->CSR conversion torch.sparse.mm performs on every call
 // (reference modules/layers.py:164,167,962).
 #include <algorithm>
+#include <climits>
+#include <cstdint>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -87,6 +89,12 @@ struct HostRb {
   std::vector<uint32_t> tp_off;
   int32_t tile_deps_max = 0;
   std::vector<int32_t> tdep_ptr, tdep_idx;
+  // Two-phase staging of the chain kernel (0 = none): the pieces of the run of source rows that holds the tile's own rows come
+  // first in the tile's piece list ("group A": half of the gathered rows, 2-3 boxes out of ~22), every row-block's panel
+  // lists the entries that gather from group A first, and the first `steps_a[w]` entry steps of compute warp w touch nothing
+  // else — the entry loop starts on them while the other boxes are still being issued / in flight.
+  // packed: pieces of A | rows of A << 8 | steps_a[0] << 16 | steps_a[1] << 24
+  std::vector<uint32_t> tile_split;
 };
 
 static void build_tiles(HostRb& rb) {
@@ -134,23 +142,73 @@ static void build_tiles(HostRb& rb) {
     rb.tpc_ptr[t + 1] = static_cast<int32_t>(rb.tpc_row.size());
     rb.tile_pieces_max = std::max(rb.tile_pieces_max, rb.tpc_ptr[t + 1] - rb.tpc_ptr[t]);
   }
+  // Group A of every tile (see HostRb::tile_split): local row range [a_lo, a_hi] of the run that holds the tile's own first
+  // row, its pieces moved to the front of the tile's piece list.  (Natural order only; a tile without such a run has no A.)
+  std::vector<int32_t> a_lo(static_cast<size_t>(rb.n_tiles), 0), a_hi(static_cast<size_t>(rb.n_tiles), -1);
+  std::vector<int32_t> a_pieces(static_cast<size_t>(rb.n_tiles), 0);
+  if (rb.perm.empty()) {
+    std::vector<std::pair<int32_t, uint32_t>> front, back;
+    for (int32_t t = 0; t < rb.n_tiles; ++t) {
+      const int32_t r0 = rb.tile_ptr[t], r1 = rb.tile_ptr[t + 1];
+      const int32_t own = t * DSW_TILE_BLOCKS * rb.R;
+      const auto it = std::lower_bound(rb.tile_row.begin() + r0, rb.tile_row.begin() + r1, own);
+      if (it == rb.tile_row.begin() + r1 || *it != own) continue;
+      int32_t lo = static_cast<int32_t>(it - rb.tile_row.begin()), hi = lo;
+      while (lo > r0 && rb.tile_row[lo - 1] + 1 == rb.tile_row[lo]) --lo;
+      while (hi + 1 < r1 && rb.tile_row[hi + 1] == rb.tile_row[hi] + 1) ++hi;
+      if (hi - lo + 1 > 255 || hi - lo + 1 == r1 - r0) continue;  // (everything in one run: nothing to overlap)
+      front.clear(), back.clear();
+      for (int32_t i = rb.tpc_ptr[t]; i < rb.tpc_ptr[t + 1]; ++i) {
+        const int32_t first = static_cast<int32_t>(rb.tpc_meta[i] >> 8) + r0;
+        (first >= lo && first <= hi ? front : back).emplace_back(rb.tpc_row[i], rb.tpc_meta[i]);
+      }
+      if (front.empty() || front.size() > 255) continue;
+      int32_t i = rb.tpc_ptr[t];
+      for (const auto& pc : front) rb.tpc_row[i] = pc.first, rb.tpc_meta[i] = pc.second, ++i;
+      for (const auto& pc : back) rb.tpc_row[i] = pc.first, rb.tpc_meta[i] = pc.second, ++i;
+      a_lo[t] = lo - r0, a_hi[t] = hi - r0, a_pieces[t] = static_cast<int32_t>(front.size());
+    }
+  }
   // entry-major padded panels
   rb.tp_ptr.assign(static_cast<size_t>(rb.n_tiles) + 1, 0);
+  rb.tile_split.assign(static_cast<size_t>(rb.n_tiles), 0u);
+  std::vector<int32_t> ord;
   for (int32_t t = 0; t < rb.n_tiles; ++t) {
     const int32_t b0 = t * DSW_TILE_BLOCKS, b1 = std::min(rb.n_blocks, b0 + DSW_TILE_BLOCKS);
     int32_t len = 0;
     for (int32_t b = b0; b < b1; ++b) len = std::max(len, rb.blkptr[b + 1] - rb.blkptr[b]);
     rb.tile_len_max = std::max(rb.tile_len_max, len);
     const size_t base = static_cast<size_t>(rb.tp_ptr[t]) * DSW_TILE_BLOCKS;
-    // the tile's panels end with DSW_PANEL_PAD all-zero steps, so that one bulk copy stages them ready to use
+    const bool split = a_hi[t] >= a_lo[t];
+    // the tile's panels end with DSW_PANEL_PAD all-zero steps, so that one bulk copy stages them ready to use; padding steps
+    // (zero weights) read a row of group A, which has always landed when a step runs
     rb.tp_val.resize((base + static_cast<size_t>(len + DSW_PANEL_PAD) * DSW_TILE_BLOCKS) * 4, 0.f);
-    rb.tp_off.resize(base + static_cast<size_t>(len + DSW_PANEL_PAD) * DSW_TILE_BLOCKS, 0u);
-    for (int32_t b = b0; b < b1; ++b)
-      for (int32_t e = rb.blkptr[b], u = 0; e < rb.blkptr[b + 1]; ++e, ++u) {
+    rb.tp_off.resize(base + static_cast<size_t>(len + DSW_PANEL_PAD) * DSW_TILE_BLOCKS, split ? static_cast<uint32_t>(a_lo[t]) * 256u : 0u);
+    int32_t steps_a[2] = {INT32_MAX, INT32_MAX}, steps[2] = {0, 0};
+    for (int32_t b = b0; b < b1; ++b) {
+      // entries that gather from group A first (stable: ascending columns inside each part)
+      ord.clear();
+      for (int32_t e = rb.blkptr[b]; e < rb.blkptr[b + 1]; ++e)
+        if (split && rb.lidx[e] >= a_lo[t] && rb.lidx[e] <= a_hi[t]) ord.push_back(e);
+      const int32_t n_a = static_cast<int32_t>(ord.size());
+      for (int32_t e = rb.blkptr[b]; e < rb.blkptr[b + 1]; ++e)
+        if (!(split && rb.lidx[e] >= a_lo[t] && rb.lidx[e] <= a_hi[t])) ord.push_back(e);
+      const int32_t n_all = static_cast<int32_t>(ord.size());
+      const int w = (b - b0) / (DSW_TILE_BLOCKS / 2);
+      steps[w] = std::max(steps[w], n_all);
+      if (n_a < n_all) steps_a[w] = std::min(steps_a[w], n_a);  // (a row-block gathering from A only constrains nothing)
+      for (int32_t u = 0; u < n_all; ++u) {
+        const int32_t e = ord[u];
         const size_t at = base + static_cast<size_t>(u) * DSW_TILE_BLOCKS + (b - b0);
         for (int r = 0; r < 4; ++r) rb.tp_val[at * 4 + r] = rb.uval[static_cast<size_t>(e) * 4 + r];
         rb.tp_off[at] = static_cast<uint32_t>(rb.lidx[e]) * 256u;
       }
+    }
+    if (split) {
+      uint32_t sa[2];
+      for (int w = 0; w < 2; ++w) sa[w] = static_cast<uint32_t>(std::min({steps_a[w], (steps[w] + 1) & ~1, 254})) & ~1u;
+      rb.tile_split[t] = static_cast<uint32_t>(a_pieces[t]) | static_cast<uint32_t>(a_hi[t] - a_lo[t] + 1) << 8 | sa[0] << 16 | sa[1] << 24;
+    }
     rb.tp_ptr[t + 1] = rb.tp_ptr[t] + len + DSW_PANEL_PAD;
   }
   // Tile dependencies of the fused chain kernel: tile t of hop k may start once hop k-1 has finished every tile
@@ -448,7 +506,7 @@ static cudaError_t upload_rb(dsw_rb* d, const HostRb& h, cudaStream_t st, bool s
             const int32_t blk = t * DSW_TILE_BLOCKS + sl;
             if (blk < h.n_blocks) wl[sl / (DSW_TILE_BLOCKS / 2)] = std::max(wl[sl / (DSW_TILE_BLOCKS / 2)], h.blkptr[blk + 1] - h.blkptr[blk]);
           }
-          meta[2 * t + 1] = make_int4(nd, (wl[0] + 1) & ~1, (wl[1] + 1) & ~1, 0);
+          meta[2 * t + 1] = make_int4(nd, (wl[0] + 1) & ~1, (wl[1] + 1) & ~1, static_cast<int32_t>(h.tile_split[t]));
           for (int32_t i = 0; i < np; ++i)
             pcs[static_cast<size_t>(t) * h.tile_pieces_max + i] =
                 make_int2(static_cast<int32_t>(h.tpc_meta[h.tpc_ptr[t] + i]), h.tpc_row[h.tpc_ptr[t] + i]);
