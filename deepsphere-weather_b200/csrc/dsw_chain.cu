@@ -26,8 +26,10 @@
 //               register-tiled loop of hop_team_kernel (dsw_spmm.cu).  They only ever wait on mbarriers.
 //   warps 0-3   one issuer warp per team, running one item ahead of it: claim, decode, the tile's metadata (one
 //               round trip: fixed-stride plan tables), dependency flags (a second one); the moment the team's
-//               entry loop ends it issues the transfers — the tile's weight / offset panels (two bulk copies) and the
-//               distinct source rows the tile gathers (one tensor-map box per run of consecutive rows).
+//               entry loop ends it posts the descriptor (`ready`: the team starts its Z / G loads) and issues the transfers —
+//               the tile's weight / offset panels (two bulk copies) and the distinct source rows the tile gathers (one
+//               tensor-map box per run of consecutive rows), in two phases: the run that holds the tile's own rows lands on
+//               `full` with the panels, the other rows on `full2`; the entry loop starts on the steps that need only the former.
 //   warp 4      publisher: collects the items whose stores have been issued and releases their flags behind ONE
 //               gpu-scope fence per round (a MEMBAR.ALL.GPU costs ~7k cycles on a busy SM: it must not sit on a
 //               compute or issuer warp's path).
@@ -180,7 +182,7 @@ struct ItemDesc {
 
 // mbarriers of one team
 struct TeamBars {
-  uint64_t ready;  // issuer -> team: descriptor written, dependencies met, transfers issued (count 1)
+  uint64_t ready;  // issuer -> team: descriptor written, dependencies met, transfers about to be issued (count 1)
   uint64_t full;   // transfers -> team: the panels and the rows of group A have landed (count 1 + tx bytes)
   uint64_t full2;  // transfers -> team: the other rows have landed (count 1 + tx bytes)
   uint64_t empty;  // team -> issuer: the entry loop is over, the buffers may be overwritten (count 64: every lane)
