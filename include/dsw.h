@@ -278,7 +278,9 @@ enum {
   DSW_OPT_L2_CHUNK_BYTES = 1, /* working-set budget (bytes) of L2-resident sample chunks; 0 / 1 = chunking off (default) */
   DSW_OPT_DEBUG = 2,          /* timing experiments only (results become wrong): 1 = hops skip staging, 2 = hops skip the FMA loop;
                                  dense kernels, bit mask: 16 = no output stores, 32 = no A transfers, 64 = no B transfers,
-                                 128 = no bf16 conversion, 256 = no MMAs; 1024 = A/B (results stay right): no L2 prefetch of the mix epilogue's addend */
+                                 128 = no bf16 conversion, 256 = no MMAs; 1024 = A/B (results stay right): no L2 prefetch of the mix epilogue's addend;
+                                 chain kernel, bit mask: 4 = phase counters, 8 = no stores, 16 = no Z loads, 32 = claim one item further
+                                 ahead, 64 = relaxed `done` arrival; 4096 = A/B (results stay right): no two-phase staging */
   DSW_OPT_NO_TMA = 3,         /* 1 = stage tiles with cp.async / register loads instead of tensor-map TMA */
   DSW_OPT_FWD_ALGO = 4,       /* 0 = auto by channel counts, 1 = TERMS (hops on Fin, then mix), 2 = CLENSHAW (mix, then hops on Fout) */
   DSW_OPT_BWD_ALGO = 5,       /* 0 = auto, 1 = TERMS (hops on dy, Fout channels), 2 = CLENSHAW (hops on Fin channels) */
