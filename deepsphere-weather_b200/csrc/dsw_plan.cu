@@ -207,7 +207,16 @@ static void build_tiles(HostRb& rb) {
     if (split) {
       uint32_t sa[2];
       for (int w = 0; w < 2; ++w) sa[w] = static_cast<uint32_t>(std::min({steps_a[w], (steps[w] + 1) & ~1, 254})) & ~1u;
-      rb.tile_split[t] = static_cast<uint32_t>(a_pieces[t]) | static_cast<uint32_t>(a_hi[t] - a_lo[t] + 1) << 8 | sa[0] << 16 | sa[1] << 24;
+      // safety net for the invariant the kernel relies on (a step of the first phase must not touch a row that lands on the
+      // second barrier): re-read the panel just written; a tile that violates it is staged in one phase
+      bool holds = true;
+      for (int32_t sl = 0; sl < b1 - b0 && holds; ++sl)
+        for (uint32_t u = 0; u < sa[sl / (DSW_TILE_BLOCKS / 2)] && holds; ++u) {
+          const int32_t local = static_cast<int32_t>(rb.tp_off[base + static_cast<size_t>(u) * DSW_TILE_BLOCKS + sl] / 256u);
+          holds = local >= a_lo[t] && local <= a_hi[t];
+        }
+      if (holds)
+        rb.tile_split[t] = static_cast<uint32_t>(a_pieces[t]) | static_cast<uint32_t>(a_hi[t] - a_lo[t] + 1) << 8 | sa[0] << 16 | sa[1] << 24;
     }
     rb.tp_ptr[t + 1] = rb.tp_ptr[t] + len + DSW_PANEL_PAD;
   }
